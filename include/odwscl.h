@@ -1,0 +1,164 @@
+/*
+ * odwscl.h -- C ABI of libodwscl_sm100.so: the B200 (sm_100a) kernels behind the OD-WSCL
+ * proposal-feature hot path.  This is the drop-in boundary: every entry point replaces a
+ * reference interface (cited per function, paths relative to the reference's wetectron/).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch types.  All data pointers are DEVICE
+ *     pointers to contiguous row-major buffers owned by the caller; the library allocates
+ *     nothing and keeps no global mutable state.  Scratch space is passed in (`ws`), sized by
+ *     the matching *_ws_bytes() query.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Kernels are only
+ *     enqueued; nothing synchronises the host.
+ *   - Return value: 0 on success, a cudaError_t value (>0) when a launch fails, or a negative
+ *     ODWSCL_E* code for argument errors.  odwscl_strerror() turns either into text.  The Python
+ *     binding raises RuntimeError on non-zero (the reference raises through AT_ASSERTM /
+ *     THCudaCheck, csrc/cuda/ROIPool_cuda.cu:115-116,151).
+ *   - Empty problems (R == 0, n == 0 ...) return 0 without launching
+ *     (csrc/cuda/ROIPool_cuda.cu:132-135,180-183).
+ */
+#ifndef ODWSCL_H_
+#define ODWSCL_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ODWSCL_VERSION 100
+#define ODWSCL_EINVAL (-1)   /* bad argument (null pointer, negative size, unsupported shape) */
+#define ODWSCL_ENOWS  (-2)   /* workspace too small */
+#define ODWSCL_SIM_DIM 128   /* embedding width of Sim_Net (sim_head/sim_net.py:13-16) */
+
+typedef void* odwscl_stream_t;
+
+int odwscl_version(void);
+const char* odwscl_strerror(int code);
+
+/* ---- A3: ROIPool forward.  Replaces _C.roi_pool_forward (csrc/ROIPool.h:11-24 ->
+ * csrc/cuda/ROIPool_cuda.cu:16-77,110-153).  feat [B,C,H,W] fp32 NCHW; rois [R,5] =
+ * (batch, x1,y1,x2,y2) image pixels; out [R,C,ph,pw] fp32; argmax [R,C,ph,pw] int32 =
+ * h*W+w inside the (b,c) plane or -1.  Bit-exact with the reference rule (Appendix B).
+ * The 7x7 / C%4==0 fast path transposes the map to channels-last inside `ws`. */
+size_t odwscl_roi_pool_fwd_ws_bytes(int B, int C, int H, int W, int R, int ph, int pw);
+int odwscl_roi_pool_fwd_f32(const float* feat, int B, int C, int H, int W, const float* rois, int R,
+                            float scale, int ph, int pw, float* out, int32_t* argmax,
+                            void* ws, size_t ws_bytes, odwscl_stream_t stream);
+
+/* ---- A4: ROIPool backward.  Replaces _C.roi_pool_backward (csrc/ROIPool.h:26-45 ->
+ * csrc/cuda/ROIPool_cuda.cu:79-108,156-202).  grad_in [B,C,H,W] is zeroed inside. */
+int odwscl_roi_pool_bwd_f32(const float* grad_out, const int32_t* argmax, const float* rois, int R,
+                            int B, int C, int H, int W, int ph, int pw, float* grad_in,
+                            odwscl_stream_t stream);
+
+/* ---- A5: ROIAlign (legacy, non-aligned).  Replaces _C.roi_align_forward/backward
+ * (csrc/ROIAlign.h:11-45 -> csrc/cuda/ROIAlign_cuda.cu:64-122,177-254). */
+int odwscl_roi_align_fwd_f32(const float* feat, int B, int C, int H, int W, const float* rois, int R,
+                             float scale, int ph, int pw, int sampling_ratio, float* out,
+                             odwscl_stream_t stream);
+int odwscl_roi_align_bwd_f32(const float* grad_out, const float* rois, int R, float scale, int ph,
+                             int pw, int B, int C, int H, int W, int sampling_ratio, float* grad_in,
+                             odwscl_stream_t stream);
+
+/* ---- A9: pairwise IoU.  plus_one=1 replaces boxlist_iou (structures/boxlist_ops.py:127-160,
+ * legacy +1 pixel convention); plus_one=0 is torchvision's convention.  out [na,nb]. */
+int odwscl_box_iou_f32(const float* a, int na, const float* b, int nb, int plus_one, float* out,
+                       odwscl_stream_t stream);
+
+/* ---- A10: NMS with torchvision.ops.nms semantics (structures/boxlist_ops.py:57): stable
+ * descending sort, IoU without +1, suppress iff IoU > thr, kept ids in descending-score order.
+ * keep [n] int64 and n_keep [1] int32 are device buffers; no host sweep, no sync.  n <= 8192. */
+int odwscl_nms_f32(const float* boxes, const float* scores, int n, float thr, int64_t* keep,
+                   int32_t* n_keep, odwscl_stream_t stream);
+/* `_C.nms` (csrc/nms.h:10-28 -> csrc/cuda/nms.cu:23-130): +1 convention, suppress iff IoU > thr,
+ * kept ids returned ASCENDING. */
+int odwscl_nms_legacy_f32(const float* boxes, const float* scores, int n, float thr, int64_t* keep,
+                          int32_t* n_keep, odwscl_stream_t stream);
+
+/* ---- A11: object discovery (roi_heads/weak_head/loss.py:271-345).
+ * A "pair" is one (image b, positive class c); pairs are listed image-major, class-ascending.
+ *   boxes [R,4]; img_off [B+1] row offsets; scores[3] = the three supervisor score tensors
+ *   [R,C] (final_score, softmax(ref1), softmax(ref2)); pair_img / pair_cls [P] (cls 0-based,
+ *   background excluded); Ncap = max proposals per image.
+ * Phase A (loss.py:281-307): per pair the union over the 3 branches of
+ *   { j : IoU+1(P[j], P[argmax_j score]) >= thres }.
+ *   out: amax [P,3] int32 (image-local argmax per branch), member [P,Ncap] uint8,
+ *        cntA [P] int32, offA [P+1] int32 (exclusive prefix of cntA; offA[P] = K),
+ *        rowsA [>= sum cntA] int32 GLOBAL row ids, pair-major ascending,
+ *        hardA [same] fp32 = S0[row,c+1] / sum_j S0[j,c+1] (loss.py:294), colsum [P] fp32. */
+int odwscl_discover_phase_a_f32(const float* boxes, const int32_t* img_off, int B, int R, int C,
+                                const float* s0, const float* s1, const float* s2,
+                                const int32_t* pair_img, const int32_t* pair_cls, int P, int Ncap,
+                                float thres, int32_t* amax, uint8_t* member, int32_t* cntA,
+                                int32_t* offA, int32_t* rowsA, float* hardA, float* colsum,
+                                odwscl_stream_t stream);
+/* Phase B (loss.py:311-345): per pair and branch: similarity rows of the top proposal(s),
+ * tau = mean(F[m] . coll[c]^T), the `>= tau` / bool-vs-float rule, torchvision NMS, fallback,
+ * set difference against the running membership.  F [R,128]; E [2K,128] = embeddings of the
+ * drop / noise augmented Phase-A positives (first K rows drop, next K rows noise, both in
+ * rowsA order).  out: inst [P,3,Ncap] int32 image-local ids in descending-score order +
+ * inst_cnt [P,3]; newl [P,3,Ncap] int32 ascending + new_cnt [P,3]; hardB [P,3,Ncap] fp32;
+ * tau_out [P,3] fp32 (diagnostic).  sim_rows_in: optional [P,3,Ncap] fp32 override of the
+ * m-row similarities (stage-wise parity tests feed the oracle's rows); NULL in production. */
+int odwscl_discover_phase_b_f32(const float* boxes, const int32_t* img_off, int B, int R, int C,
+                                const float* s0, const float* s1, const float* s2,
+                                const int32_t* pair_img, const int32_t* pair_cls, int P, int Ncap,
+                                const float* F, const float* E, const int32_t* amax,
+                                uint8_t* member, const int32_t* cntA, const int32_t* offA,
+                                const int32_t* rowsA, const float* colsum, float nms_thr,
+                                int32_t* inst, int32_t* inst_cnt, int32_t* newl, int32_t* new_cnt,
+                                float* hardB, float* tau_out, const float* sim_rows_in,
+                                odwscl_stream_t stream);
+/* Bank assembly for SupConLossV2 (sim_head/sim_loss.py:55-58 + loss.py:290-345 append order):
+ * rows class-major, weights in execution order (the reference's misalignment is reproduced).
+ * row_src [Mcap] int32: < R -> row of F, else R + row of E; row_lab [Mcap] int32; row_w [Mcap];
+ * M_out [1] int32. */
+int odwscl_bank_assemble(const int32_t* pair_img, const int32_t* pair_cls, int P, int B, int R,
+                         int Ncap, int num_fg_classes, const int32_t* img_off, const int32_t* cntA,
+                         const int32_t* offA, const int32_t* rowsA, const float* hardA,
+                         const int32_t* newl, const int32_t* new_cnt, const float* hardB, int Mcap,
+                         int32_t* row_src, int32_t* row_lab, float* row_w, int32_t* M_out,
+                         odwscl_stream_t stream);
+
+/* ---- A12: SupConLossV2 forward / backward (sim_head/sim_loss.py:49-80), fused: the M x M
+ * similarity tile product, masked exp row sums and the weighted log ratio never leave the SM.
+ * V = [F ; E] addressed through row_src; M read from device (M_dev) so no host sync is needed.
+ * stats [Mcap,4] fp32 (row max, pos sum, all sum, row loss); loss_out [1] fp32 = mean_r(...). */
+int odwscl_supcon_fwd_f32(const float* F, const float* E, int R, const int32_t* row_src,
+                          const int32_t* row_lab, const float* row_w, const int32_t* M_dev, int Mcap,
+                          float inv_temp, float* stats, float* loss_out, odwscl_stream_t stream);
+/* dF [R,128] and dE [nE,128] are ACCUMULATED into (caller zeroes); gscale = upstream grad. */
+int odwscl_supcon_bwd_f32(const float* F, const float* E, int R, const int32_t* row_src,
+                          const int32_t* row_lab, const float* row_w, const int32_t* M_dev, int Mcap,
+                          float inv_temp, const float* stats, const float* gscale_dev, float* dF,
+                          float* dE, odwscl_stream_t stream);
+
+/* ---- A13: od_layer (weak_head/pseudo_label_generator.py:135-197): per (image, branch) the
+ * pseudo-GT set from `inst`, IoU+1 N x G with first-max argmax on device (no numpy round trip),
+ * labels (bg iff max <= fg_thr), weights, BoxCoder(10,10,5,5).encode targets
+ * (modeling/box_coder.py:22-50).  labels [3,R] int64, weights [3,R], targets [3,R,4]. */
+int odwscl_od_layer_f32(const float* boxes, const int32_t* img_off, int B, int R, int C,
+                        const float* s0, const float* s1, const float* s2, const int32_t* pair_img,
+                        const int32_t* pair_cls, int P, int Ncap, const int32_t* inst,
+                        const int32_t* inst_cnt, float fg_thr, int64_t* labels, float* weights,
+                        float* targets, odwscl_stream_t stream);
+
+/* ---- A15: DropBlock2D apply (modeling/dropblock/drop_block.py:29-66) with a device-sampled
+ * centre mask [R,ph,pw] (1.0 = drop centre): block mask by block x block dilation, global
+ * renormalisation numel/sum, y = x * mask * scale in ONE pass over x [R,C,ph,pw].
+ * scale_io [2] fp32: [0] = sum(block_mask), [1] = numel/sum.  reuse_scale != 0 skips the
+ * reduction and applies the stored scale (the backward: dx = dy * mask * scale). */
+int odwscl_dropblock_f32(const float* x, const float* centres, int R, int C, int ph, int pw,
+                         int block, float* y, float* scale_io, int reuse_scale,
+                         odwscl_stream_t stream);
+
+/* ---- A11 (drop-in for loss.py:319): full N x N similarity F F^T on the tensor cores
+ * (tcgen05, 3xTF32 split so the result is fp32-accurate).  out [N,N] fp32. */
+int odwscl_sim_nxn_f32(const float* F, int N, float* out, odwscl_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ODWSCL_H_ */

@@ -1,0 +1,302 @@
+"""ctypes binding of libodwscl_sm100.so (include/odwscl.h).
+
+PyTorch is plumbing here: it owns device memory and the current stream; every call passes raw
+device pointers + sizes + the stream handle through the C ABI.  There is NO fallback: if the
+library is missing or a call fails, a RuntimeError is raised (the reference raises through
+AT_ASSERTM / THCudaCheck, csrc/cuda/ROIPool_cuda.cu:115-116,151).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_float, c_int, c_size_t, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libodwscl_sm100.so")
+_lib = None
+launch_count = 0          # kernels-launching C-ABI calls made so far (bench.py reports it)
+
+# kernels enqueued per entry point (for the `gpu_launches` bench key)
+_LAUNCHES = {
+    "odwscl_roi_pool_fwd_f32": 2, "odwscl_roi_pool_bwd_f32": 1, "odwscl_roi_align_fwd_f32": 1,
+    "odwscl_roi_align_bwd_f32": 1, "odwscl_box_iou_f32": 1, "odwscl_nms_f32": 1, "odwscl_nms_legacy_f32": 1,
+    "odwscl_discover_phase_a_f32": 2, "odwscl_discover_phase_b_f32": 1, "odwscl_bank_assemble": 1,
+    "odwscl_supcon_fwd_f32": 2, "odwscl_supcon_bwd_f32": 1, "odwscl_od_layer_f32": 1,
+    "odwscl_dropblock_f32": 3, "odwscl_sim_nxn_f32": 1,
+}
+
+_P, _I, _F, _Z = c_void_p, c_int, c_float, c_size_t
+_SIGS = {
+    "odwscl_roi_pool_fwd_ws_bytes": (_Z, [_I] * 7),
+    "odwscl_roi_pool_fwd_f32": (_I, [_P, _I, _I, _I, _I, _P, _I, _F, _I, _I, _P, _P, _P, _Z, _P]),
+    "odwscl_roi_pool_bwd_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "odwscl_roi_align_fwd_f32": (_I, [_P, _I, _I, _I, _I, _P, _I, _F, _I, _I, _I, _P, _P]),
+    "odwscl_roi_align_bwd_f32": (_I, [_P, _P, _I, _F, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "odwscl_box_iou_f32": (_I, [_P, _I, _P, _I, _I, _P, _P]),
+    "odwscl_nms_f32": (_I, [_P, _P, _I, _F, _P, _P, _P]),
+    "odwscl_nms_legacy_f32": (_I, [_P, _P, _I, _F, _P, _P, _P]),
+    "odwscl_discover_phase_a_f32": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _I, _F] + [_P] * 7 + [_P]),
+    "odwscl_discover_phase_b_f32": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _I] + [_P] * 8 + [_F] + [_P] * 7 + [_P]),
+    "odwscl_bank_assemble": (_I, [_P, _P, _I, _I, _I, _I, _I] + [_P] * 8 + [_I] + [_P] * 4 + [_P]),
+    "odwscl_supcon_fwd_f32": (_I, [_P, _P, _I, _P, _P, _P, _P, _I, _F, _P, _P, _P]),
+    "odwscl_supcon_bwd_f32": (_I, [_P, _P, _I, _P, _P, _P, _P, _I, _F, _P, _P, _P, _P, _P]),
+    "odwscl_od_layer_f32": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _I, _P, _P, _F, _P, _P, _P, _P]),
+    "odwscl_dropblock_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P]),
+    "odwscl_sim_nxn_f32": (_I, [_P, _I, _P, _P]),
+    "odwscl_version": (_I, []),
+    "odwscl_strerror": (ctypes.c_char_p, [_I]),
+}
+EXPORTS = tuple(_SIGS)
+
+
+def lib():
+    """Load the C-ABI library; fail loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libodwscl_sm100.so is missing (%s): build it with `python od-wscl_b200/csrc/build.py`; "
+                "there is no CPU / eager fallback for the hot path" % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def _stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    return c_void_p(t.data_ptr())
+
+
+def _call(name, *args):
+    global launch_count
+    rc = getattr(lib(), name)(*args)
+    if rc != 0:
+        raise RuntimeError("%s failed: %s (%d)" % (name, lib().odwscl_strerror(rc).decode(), rc))
+    launch_count += _LAUNCHES.get(name, 0)
+
+
+def _chk(t, dtype, name):
+    if not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor (no CPU implementation: csrc/ROIPool.h:23)" % name)
+    if t.dtype != dtype:
+        raise RuntimeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    return t.contiguous()
+
+
+_ws_cache = {}
+
+
+def _workspace(nbytes, device):
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+# ------------------------------------------------------------------------------------------
+def roi_pool_forward(feat, rois, scale, ph, pw):
+    feat, rois = _chk(feat, torch.float32, "input"), _chk(rois, torch.float32, "rois")
+    B, C, H, W = feat.shape
+    R = rois.shape[0]
+    out = torch.empty((R, C, ph, pw), dtype=torch.float32, device=feat.device)
+    arg = torch.empty((R, C, ph, pw), dtype=torch.int32, device=feat.device)
+    if out.numel() == 0:
+        return out, arg
+    with torch.cuda.device(feat.device):
+        n = lib().odwscl_roi_pool_fwd_ws_bytes(B, C, H, W, R, ph, pw)
+        ws = _workspace(n, feat.device)
+        _call("odwscl_roi_pool_fwd_f32", _ptr(feat), B, C, H, W, _ptr(rois), R, float(scale), ph, pw,
+              _ptr(out), _ptr(arg), _ptr(ws), ws.numel(), _stream())
+    return out, arg
+
+
+def roi_pool_backward(grad, rois, argmax, ph, pw, B, C, H, W):
+    grad, rois = _chk(grad, torch.float32, "grad"), _chk(rois, torch.float32, "rois")
+    argmax = _chk(argmax, torch.int32, "argmax")
+    gin = torch.empty((B, C, H, W), dtype=torch.float32, device=grad.device)
+    with torch.cuda.device(grad.device):
+        _call("odwscl_roi_pool_bwd_f32", _ptr(grad), _ptr(argmax), _ptr(rois), rois.shape[0], B, C, H, W, ph, pw,
+              _ptr(gin), _stream())
+    return gin
+
+
+def roi_align_forward(feat, rois, scale, ph, pw, sampling_ratio):
+    feat, rois = _chk(feat, torch.float32, "input"), _chk(rois, torch.float32, "rois")
+    B, C, H, W = feat.shape
+    out = torch.empty((rois.shape[0], C, ph, pw), dtype=torch.float32, device=feat.device)
+    with torch.cuda.device(feat.device):
+        _call("odwscl_roi_align_fwd_f32", _ptr(feat), B, C, H, W, _ptr(rois), rois.shape[0], float(scale), ph, pw,
+              int(sampling_ratio), _ptr(out), _stream())
+    return out
+
+
+def roi_align_backward(grad, rois, scale, ph, pw, B, C, H, W, sampling_ratio):
+    grad, rois = _chk(grad, torch.float32, "grad"), _chk(rois, torch.float32, "rois")
+    gin = torch.empty((B, C, H, W), dtype=torch.float32, device=grad.device)
+    with torch.cuda.device(grad.device):
+        _call("odwscl_roi_align_bwd_f32", _ptr(grad), _ptr(rois), rois.shape[0], float(scale), ph, pw, B, C, H, W,
+              int(sampling_ratio), _ptr(gin), _stream())
+    return gin
+
+
+def box_iou(a, b, plus_one=True):
+    a, b = _chk(a, torch.float32, "boxes a").view(-1, 4), _chk(b, torch.float32, "boxes b").view(-1, 4)
+    out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        _call("odwscl_box_iou_f32", _ptr(a), a.shape[0], _ptr(b), b.shape[0], int(plus_one), _ptr(out), _stream())
+    return out
+
+
+def _nms(name, boxes, scores, thr):
+    boxes, scores = _chk(boxes, torch.float32, "boxes").view(-1, 4), _chk(scores, torch.float32, "scores").view(-1)
+    n = boxes.shape[0]
+    keep = torch.empty((n,), dtype=torch.int64, device=boxes.device)
+    cnt = torch.zeros((1,), dtype=torch.int32, device=boxes.device)
+    with torch.cuda.device(boxes.device):
+        _call(name, _ptr(boxes), _ptr(scores), n, float(thr), _ptr(keep), _ptr(cnt), _stream())
+    return keep, cnt
+
+
+def nms_padded(boxes, scores, thr):
+    """torchvision-semantics NMS; returns (keep [n] padded, n_keep [1]) without synchronising."""
+    return _nms("odwscl_nms_f32", boxes, scores, thr)
+
+
+def nms(boxes, scores, thr):
+    keep, cnt = _nms("odwscl_nms_f32", boxes, scores, thr)
+    return keep[: int(cnt.item())]
+
+
+def nms_legacy(boxes, scores, thr):
+    keep, cnt = _nms("odwscl_nms_legacy_f32", boxes, scores, thr)
+    return keep[: int(cnt.item())]
+
+
+def sim_nxn(F):
+    F = _chk(F, torch.float32, "F")
+    assert F.shape[1] == 128
+    out = torch.empty((F.shape[0], F.shape[0]), dtype=torch.float32, device=F.device)
+    with torch.cuda.device(F.device):
+        _call("odwscl_sim_nxn_f32", _ptr(F), F.shape[0], _ptr(out), _stream())
+    return out
+
+
+def dropblock(x, centres, block, scale_io=None):
+    """y = x * block_mask * numel/sum.  Pass the returned scale_io back in for the backward."""
+    x, centres = _chk(x, torch.float32, "x"), _chk(centres, torch.float32, "centres")
+    R, C, ph, pw = x.shape
+    y = torch.empty_like(x)
+    reuse = scale_io is not None
+    if scale_io is None:
+        scale_io = torch.empty((2,), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _call("odwscl_dropblock_f32", _ptr(x), _ptr(centres), R, C, ph, pw, int(block), _ptr(y), _ptr(scale_io),
+              int(reuse), _stream())
+    return y, scale_io
+
+
+# ---------------------------------------------------------------- object discovery / SupCon
+class DiscoveryState:
+    """Device buffers of one object-discovery pass (sizes: P pairs, Ncap proposals per image)."""
+    pass
+
+
+def discover_phase_a(boxes, img_off, scores, pair_img, pair_cls, Ncap, thres):
+    dev = boxes.device
+    R, C = scores[0].shape
+    P = pair_img.numel()
+    B = img_off.numel() - 1
+    i32 = dict(dtype=torch.int32, device=dev)
+    st = DiscoveryState()
+    st.P, st.Ncap, st.R, st.C, st.B = P, Ncap, R, C, B
+    st.boxes, st.img_off, st.scores, st.pair_img, st.pair_cls = boxes, img_off, scores, pair_img, pair_cls
+    st.amax = torch.empty((P, 3), **i32)
+    st.member = torch.empty((P, Ncap), dtype=torch.uint8, device=dev)
+    st.cntA = torch.empty((P,), **i32)
+    st.offA = torch.empty((P + 1,), **i32)
+    st.rowsA = torch.empty((max(P * Ncap, 1),), **i32)
+    st.hardA = torch.empty((max(P * Ncap, 1),), dtype=torch.float32, device=dev)
+    st.colsum = torch.empty((P,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _call("odwscl_discover_phase_a_f32", _ptr(boxes), _ptr(img_off), B, R, C, _ptr(scores[0]), _ptr(scores[1]),
+              _ptr(scores[2]), _ptr(pair_img), _ptr(pair_cls), P, Ncap, float(thres), _ptr(st.amax),
+              _ptr(st.member), _ptr(st.cntA), _ptr(st.offA), _ptr(st.rowsA), _ptr(st.hardA), _ptr(st.colsum),
+              _stream())
+    return st
+
+
+def discover_phase_b(st, F, E, nms_thr, sim_rows_in=None):
+    dev = F.device
+    P, Ncap = st.P, st.Ncap
+    i32 = dict(dtype=torch.int32, device=dev)
+    st.inst = torch.empty((P, 3, Ncap), **i32)
+    st.inst_cnt = torch.empty((P, 3), **i32)
+    st.newl = torch.empty((P, 3, Ncap), **i32)
+    st.new_cnt = torch.empty((P, 3), **i32)
+    st.hardB = torch.empty((P, 3, Ncap), dtype=torch.float32, device=dev)
+    st.tau = torch.empty((P, 3), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _call("odwscl_discover_phase_b_f32", _ptr(st.boxes), _ptr(st.img_off), st.B, st.R, st.C, _ptr(st.scores[0]),
+              _ptr(st.scores[1]), _ptr(st.scores[2]), _ptr(st.pair_img), _ptr(st.pair_cls), P, Ncap, _ptr(F),
+              _ptr(E), _ptr(st.amax), _ptr(st.member), _ptr(st.cntA), _ptr(st.offA), _ptr(st.rowsA),
+              _ptr(st.colsum), float(nms_thr), _ptr(st.inst), _ptr(st.inst_cnt), _ptr(st.newl), _ptr(st.new_cnt),
+              _ptr(st.hardB), _ptr(st.tau), _ptr(sim_rows_in), _stream())
+    return st
+
+
+def bank_assemble(st, num_fg_classes, Mcap):
+    dev = st.boxes.device
+    st.Mcap = Mcap
+    st.row_src = torch.empty((max(Mcap, 1),), dtype=torch.int32, device=dev)
+    st.row_lab = torch.empty((max(Mcap, 1),), dtype=torch.int32, device=dev)
+    st.row_w = torch.empty((max(Mcap, 1),), dtype=torch.float32, device=dev)
+    st.M = torch.zeros((1,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _call("odwscl_bank_assemble", _ptr(st.pair_img), _ptr(st.pair_cls), st.P, st.B, st.R, st.Ncap,
+              int(num_fg_classes), _ptr(st.img_off), _ptr(st.cntA), _ptr(st.offA), _ptr(st.rowsA), _ptr(st.hardA),
+              _ptr(st.newl), _ptr(st.new_cnt), _ptr(st.hardB), Mcap, _ptr(st.row_src), _ptr(st.row_lab),
+              _ptr(st.row_w), _ptr(st.M), _stream())
+    return st
+
+
+def supcon_forward(F, E, row_src, row_lab, row_w, M_dev, Mcap, inv_temp):
+    dev = F.device
+    stats = torch.empty((max(Mcap, 1), 4), dtype=torch.float32, device=dev)
+    loss = torch.zeros((1,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _call("odwscl_supcon_fwd_f32", _ptr(F), _ptr(E), F.shape[0], _ptr(row_src), _ptr(row_lab), _ptr(row_w),
+              _ptr(M_dev), Mcap, float(inv_temp), _ptr(stats), _ptr(loss), _stream())
+    return loss, stats
+
+
+def supcon_backward(F, E, row_src, row_lab, row_w, M_dev, Mcap, inv_temp, stats, gscale):
+    dF = torch.zeros_like(F)
+    dE = torch.zeros_like(E) if E is not None and E.numel() else None
+    with torch.cuda.device(F.device):
+        _call("odwscl_supcon_bwd_f32", _ptr(F), _ptr(E), F.shape[0], _ptr(row_src), _ptr(row_lab), _ptr(row_w),
+              _ptr(M_dev), Mcap, float(inv_temp), _ptr(stats), _ptr(gscale), _ptr(dF), _ptr(dE), _stream())
+    return dF, dE
+
+
+def od_layer(st, fg_thr):
+    dev = st.boxes.device
+    labels = torch.empty((3, st.R), dtype=torch.int64, device=dev)
+    weights = torch.empty((3, st.R), dtype=torch.float32, device=dev)
+    targets = torch.empty((3, st.R, 4), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _call("odwscl_od_layer_f32", _ptr(st.boxes), _ptr(st.img_off), st.B, st.R, st.C, _ptr(st.scores[0]),
+              _ptr(st.scores[1]), _ptr(st.scores[2]), _ptr(st.pair_img), _ptr(st.pair_cls), st.P, st.Ncap,
+              _ptr(st.inst), _ptr(st.inst_cnt), float(fg_thr), _ptr(labels), _ptr(weights), _ptr(targets), _stream())
+    return labels, weights, targets

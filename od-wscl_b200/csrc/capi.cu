@@ -1,0 +1,12 @@
+// capi.cu -- version / error text of the C ABI (include/odwscl.h).
+#include "common.cuh"
+
+ODW_API int odwscl_version(void) { return ODWSCL_VERSION; }
+
+ODW_API const char* odwscl_strerror(int code) {
+  if (code == 0) return "ok";
+  if (code == ODWSCL_EINVAL) return "odwscl: invalid argument";
+  if (code == ODWSCL_ENOWS) return "odwscl: workspace too small";
+  if (code > 0) return cudaGetErrorString((cudaError_t)code);
+  return "odwscl: unknown error";
+}

@@ -1,0 +1,80 @@
+// dropblock.cu -- DropBlock2D apply.
+// Reference: modeling/dropblock/drop_block.py:29-66 -- CPU-sampled mask, H2D copy, max_pool2d,
+// two full elementwise passes over [R,C,7,7] (200 MB each at R=2000) plus a global reduction.
+// Here the centre mask is sampled on the device by the caller; the block mask (block x block
+// dilation of the centres, window rows y - block/2 .. y - block/2 + block - 1, as max_pool2d with
+// padding block/2 and the even-size crop of :61-62) is rebuilt per roi in shared memory and applied
+// in ONE pass:  y = x * block_mask * (numel / sum(block_mask)).
+// scale_io[0] = sum(block_mask), scale_io[1] = numel / sum.  With reuse_scale != 0 the stored scale
+// is used (backward: dx = dy * block_mask * scale).
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float block_mask_at(const float* __restrict__ cen, int ph, int pw, int block, int y,
+                                               int x) {
+  const int y0 = y - block / 2, x0 = x - block / 2;
+  float mx = 0.f;
+  for (int dy = 0; dy < block; ++dy)
+    for (int dx = 0; dx < block; ++dx) {
+      const int yy = y0 + dy, xx = x0 + dx;
+      if (yy >= 0 && yy < ph && xx >= 0 && xx < pw) mx = fmaxf(mx, cen[yy * pw + xx]);
+    }
+  return 1.f - mx;
+}
+
+__global__ void dropblock_sum_kernel(const float* __restrict__ centres, int R, int ph, int pw, int block,
+                                     float* __restrict__ scale_io) {
+  const int cells = ph * pw;
+  float part = 0.f;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < (long long)R * cells;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(t / cells), k = (int)(t % cells);
+    part += block_mask_at(centres + (size_t)r * cells, ph, pw, block, k / pw, k % pw);
+  }
+  part = odw_warp_sum(part);
+  if ((threadIdx.x & 31) == 0 && part != 0.f) atomicAdd(scale_io, part);   // integer-valued: order-free
+}
+
+__global__ void dropblock_scale_kernel(int R, int ph, int pw, float* __restrict__ scale_io) {
+  scale_io[1] = (float)((long long)R * ph * pw) / scale_io[0];
+}
+
+__global__ void __launch_bounds__(256)
+dropblock_apply_kernel(const float* __restrict__ x, const float* __restrict__ centres, int C, int ph, int pw,
+                       int block, const float* __restrict__ scale_io, float* __restrict__ y) {
+  extern __shared__ float s_bm[];
+  const int r = blockIdx.x, cells = ph * pw;
+  const float scale = scale_io[1];
+  for (int k = threadIdx.x; k < cells; k += blockDim.x)
+    s_bm[k] = block_mask_at(centres + (size_t)r * cells, ph, pw, block, k / pw, k % pw) * scale;
+  __syncthreads();
+  const size_t base = (size_t)r * C * cells;
+  const int n = C * cells;
+  for (int t = threadIdx.x; t < n; t += blockDim.x) {
+    const float v = __ldcs(x + base + t) * s_bm[t % cells];
+    __stcs(y + base + t, v);
+  }
+}
+
+}  // namespace
+
+ODW_API int odwscl_dropblock_f32(const float* x, const float* centres, int R, int C, int ph, int pw, int block,
+                                 float* y, float* scale_io, int reuse_scale, odwscl_stream_t stream) {
+  if (R < 0 || C < 0 || ph <= 0 || pw <= 0 || block <= 0) return ODWSCL_EINVAL;
+  if (R == 0 || C == 0) return 0;
+  if (!x || !centres || !y || !scale_io) return ODWSCL_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!reuse_scale) {
+    ODW_CUDA(cudaMemsetAsync(scale_io, 0, 2 * sizeof(float), st));
+    const long long total = (long long)R * ph * pw;
+    dropblock_sum_kernel<<<(int)min((long long)ODW_NUM_SMS, (total + 255) / 256), 256, 0, st>>>(centres, R, ph, pw,
+                                                                                             block, scale_io);
+    ODW_LAUNCH_CHECK();
+    dropblock_scale_kernel<<<1, 1, 0, st>>>(R, ph, pw, scale_io);
+    ODW_LAUNCH_CHECK();
+  }
+  dropblock_apply_kernel<<<R, 256, ph * pw * sizeof(float), st>>>(x, centres, C, ph, pw, block, scale_io, y);
+  ODW_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,47 @@
+"""DropBlock2D (modeling/dropblock/drop_block.py:7-71) on the device: the centre mask is sampled
+with the device generator (the reference samples on the CPU and copies, :42-45) and the block
+mask / renormalisation / multiply run as one fused pass (csrc/dropblock.cu), forward and backward."""
+import torch
+from torch import nn
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from .. import capi
+
+
+class _DropBlockFn(Function):
+    @staticmethod
+    def forward(ctx, x, centres, block):
+        y, scale_io = capi.dropblock(x, centres, block)
+        ctx.save_for_backward(centres, scale_io)
+        ctx.block = block
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        centres, scale_io = ctx.saved_tensors
+        gx, _ = capi.dropblock(gy, centres, ctx.block, scale_io)
+        return gx, None, None
+
+
+class DropBlock2D(nn.Module):
+    def __init__(self, drop_prob, block_size):
+        super().__init__()
+        self.drop_prob = drop_prob
+        self.block_size = block_size
+        self.centre_sampler = None     # test hook: callable(n, h, w, gamma, device) -> float mask
+
+    def forward(self, x):
+        assert x.dim() == 4, "Expected input with 4 dimensions (bsize, channels, height, width)"
+        if not self.training or self.drop_prob == 0.0:
+            return x
+        gamma = self.drop_prob / (self.block_size ** 2)                 # :69-70
+        n, _, h, w = x.shape
+        if n == 0:
+            return x
+        if self.centre_sampler is not None:
+            centres = self.centre_sampler(n, h, w, gamma, x.device)
+        else:
+            centres = (torch.rand(n, h, w, device=x.device) < gamma).float()   # :42
+        return _DropBlockFn.apply(x.contiguous(), centres.contiguous(), self.block_size)

@@ -1,0 +1,168 @@
+"""RoIRegLossComputation (roi_heads/weak_head/loss.py:172-411), same call signature and loss /
+accuracy keys, re-designed for the device:
+
+  reference                                           here
+  ------------------------------------------------    -------------------------------------------
+  2 triple-nested Python loops, ~20-40 tiny kernels   discover phase A / phase B kernels, one CTA
+  and >15 host syncs per (image, branch, class)       per (image, class); ONE host sync per step
+  N x N torch.mm per inner iteration (loss.py:319)    only the similarity rows the rule reads
+  torchvision NMS with a host sweep                   sort + sweep in shared memory
+  SupConLossV2: GEMM + ~12 elementwise M x M passes   fused tile kernels, fwd and bwd
+  od_layer via .cpu().numpy() (plg.py:176-177)        one kernel per (image, branch)
+  2 small fc6/fc7/Sim_Net passes per (image, class)   one batched pass over all augmented positives
+
+The single host synchronisation reads K = number of Phase-A positives (needed to size the
+augmented-positives GEMM batch)."""
+import torch
+import torch.nn.functional as F
+
+from .. import capi
+from ..config import cfg as global_cfg
+from ..layers import smooth_l1_loss
+from . import registry
+from .sim_head import SupConLossV2, supcon_bank_loss
+
+
+def _host_labels(target):
+    lab = target.get_field("labels_host") if target.has_field("labels_host") else target.get_field("labels")
+    if isinstance(lab, torch.Tensor):
+        lab = lab.cpu()
+    return sorted(set(int(x) for x in lab))
+
+
+@registry.ROI_WEAK_LOSS.register("RoIRegLoss")
+class RoIRegLossComputation(object):
+    def __init__(self, cfg):
+        self.refine_p = cfg.MODEL.ROI_WEAK_HEAD.OICR_P
+        self.contra = cfg.SOLVER.CONTRA
+        if not (self.contra and self.refine_p == 0):
+            raise NotImplementedError("only the shipped configuration (CONTRA: True, OICR_P: 0.0 -> od_layer) "
+                                      "is on the hot path (SURVEY 2.1 #7)")
+        self.cls_agnostic_bbox_reg = cfg.MODEL.CLS_AGNOSTIC_BBOX_REG
+        self.nms = cfg.nms
+        self.sim_lmda = cfg.lmda
+        self.p_thres = cfg.thres
+        self.p_iou = cfg.iou            # read but unused, as in the reference (loss.py:197-198)
+        self.temp = cfg.temp
+        if cfg.loss != "supconv2":
+            raise NotImplementedError("only cfg.loss == 'supconv2' works in the reference (SURVEY App. D)")
+        self.sim_loss = SupConLossV2(self.temp)
+        self.fg_thresh = cfg.MODEL.ROI_HEADS.FG_IOU_THRESHOLD
+        self.batch_aug = True           # False: per-(image,class) drop/noise calls in reference order (RNG replay)
+        self.last_state = None          # DiscoveryState of the last call (tests / diagnostics)
+
+    def __call__(self, class_score, det_score, ref_scores, ref_bbox_preds, sim_feature, clean_pooled_feats,
+                 feature_extractor, model_sim, proposals, targets, epsilon=1e-8):
+        sizes = [len(p) for p in proposals]
+        B, R = len(sizes), sum(sizes)
+        class_score = F.softmax(torch.cat(class_score, dim=0), dim=1)                     # loss.py:234
+        det_score = torch.cat(det_score, dim=0)
+        C = class_score.shape[1]
+        dev = class_score.device
+        same = all(s == sizes[0] for s in sizes)
+        if same:
+            final_det = F.softmax(det_score.view(B, sizes[0], C), dim=1).view(R, C)      # loss.py:237-244
+        else:
+            final_det = torch.cat([F.softmax(d, dim=0) for d in det_score.split(sizes)], dim=0)
+        final_score = class_score * final_det                                             # loss.py:246
+        ref_sm = [F.softmax(r, dim=1) for r in ref_scores]
+
+        # ---- host-side bookkeeping from the (host) image labels: pairs, offsets, multi-hot labels
+        pos = [[c - 1 for c in _host_labels(t) if c > 0] for t in targets]               # loss.py:270
+        pair_img = [b for b in range(B) for _ in pos[b]]
+        pair_cls = [c for b in range(B) for c in pos[b]]
+        P = len(pair_img)
+        offs = [0]
+        for s in sizes:
+            offs.append(offs[-1] + s)
+        meta = torch.tensor(pair_img + pair_cls + offs, dtype=torch.int32).pin_memory().to(dev, non_blocking=True)
+        pair_img_d, pair_cls_d, img_off_d = meta[:P], meta[P:2 * P], meta[2 * P:]
+        img_labels = torch.zeros((B, C), dtype=torch.float32)
+        for b in range(B):
+            for c in pos[b]:
+                img_labels[b, c + 1] = 1.0
+        img_labels_d = img_labels.pin_memory().to(dev, non_blocking=True)
+        boxes = torch.cat([p.bbox for p in proposals], dim=0).float().contiguous()
+        Ncap = max(sizes)
+
+        losses = dict(loss_img=0)
+        accs = dict(acc_img=0)
+        for i in range(3):
+            losses["loss_ref_cls%d" % i] = 0
+            losses["loss_ref_reg%d" % i] = 0
+            accs["acc_ref%d" % i] = 0
+
+        # ---- contrastive object discovery (loss.py:271-347)
+        scores = (final_score.detach().contiguous(), ref_sm[0].detach().contiguous(), ref_sm[1].detach().contiguous())
+        Fm = sim_feature.contiguous()
+        st = capi.discover_phase_a(boxes, img_off_d, scores, pair_img_d, pair_cls_d, Ncap, self.p_thres)
+        offA_h = st.offA.cpu()                                   # the one host sync of the step
+        K = int(offA_h[P]) if P > 0 else 0
+        rows = st.rowsA[:K].long()
+        if self.batch_aug:
+            X = clean_pooled_feats.index_select(0, rows)
+            aug = torch.cat([feature_extractor.drop_pool(X), feature_extractor.noise_pool(X)], dim=0)
+        else:
+            drops, noises = [], []
+            for p in range(P):
+                Xp = clean_pooled_feats.index_select(0, rows[int(offA_h[p]):int(offA_h[p + 1])])
+                drops.append(feature_extractor.drop_pool(Xp))
+                noises.append(feature_extractor.noise_pool(Xp))
+            aug = torch.cat(drops + noises, dim=0)
+        E = model_sim(feature_extractor.forward_neck(aug)).contiguous()                  # [2K,128]
+        capi.discover_phase_b(st, Fm.detach(), E.detach(), self.nms)
+        Mcap = 3 * K + 3 * sum(sizes[b] for b in pair_img)
+        capi.bank_assemble(st, C - 1, Mcap)
+        self.last_state = st
+        losses["loss_sim"] = self.sim_lmda * supcon_bank_loss(Fm, E, st.row_src, st.row_lab, st.row_w, st.M, Mcap,
+                                                              self.temp)               # loss.py:347
+
+        # ---- pseudo labels for the three refinement branches (loss.py:364-368 -> od_layer)
+        pl, lw, rt = capi.od_layer(st, self.fg_thresh)
+
+        # ---- MIL + refinement losses (loss.py:349-400), vectorised over images
+        inv_n = torch.tensor([1.0 / s for s in sizes for _ in range(s)], dtype=torch.float32).pin_memory() \
+            .to(dev, non_blocking=True) if not same else None
+
+        def per_image_mean_sum(v):          # sum_b mean_{j in image b} v_j
+            if same:
+                return v.sum() / sizes[0]
+            return (v * inv_n).sum()
+
+        if same:
+            img_score = final_score.view(B, sizes[0], C).sum(1)
+        else:
+            img_score = torch.stack([f.sum(0) for f in final_score.split(sizes)])
+        img_score = torch.clamp(img_score, min=epsilon, max=1 - epsilon)                 # loss.py:353
+        losses["loss_img"] = F.binary_cross_entropy(img_score, img_labels_d, reduction="none").mean(1).sum()
+        ar4 = torch.arange(4, device=dev)
+        for i in range(3):
+            lmda = 3 if i == 0 else 1                                                    # loss.py:373
+            ce = F.cross_entropy(ref_scores[i], pl[i], reduction="none") * lw[i]
+            losses["loss_ref_cls%d" % i] = lmda * per_image_mean_sum(ce)
+            fg = (pl[i] > 0).float()
+            map_inds = (ar4[None] + 4).expand(R, 4) if self.cls_agnostic_bbox_reg else 4 * pl[i][:, None] + ar4[None]
+            sl1 = smooth_l1_loss(ref_bbox_preds[i].gather(1, map_inds), rt[i], beta=1, reduction=False)
+            losses["loss_ref_reg%d" % i] = lmda * per_image_mean_sum((sl1 * (lw[i] * fg)[:, None]).sum(1))
+
+        with torch.no_grad():               # compute_avg_img_accuracy (loss.py:25-34) without .item()
+            for b in range(B):
+                k = max(len(pos[b]), 1)
+                lab_b = img_labels_d[b]
+                sl = slice(offs[b], offs[b + 1])
+                accs["acc_img"] = accs["acc_img"] + lab_b[img_score[b].topk(k)[1]].mean()
+                for i in range(3):
+                    rs = ref_scores[i][sl].sum(0)
+                    accs["acc_ref%d" % i] = accs["acc_ref%d" % i] + lab_b[1:][rs[1:].topk(k)[1]].mean()
+
+        for k in losses:
+            if "sim" in k:
+                continue
+            losses[k] = losses[k] / B                                                     # loss.py:403-406
+        for k in accs:
+            accs[k] = accs[k] / B
+        return losses, accs
+
+
+def make_roi_weak_loss_evaluator(cfg):
+    return registry.ROI_WEAK_LOSS[cfg.MODEL.ROI_WEAK_HEAD.LOSS](cfg)

@@ -1,0 +1,70 @@
+"""Sim_Net (roi_heads/sim_head/sim_net.py:7-26) and SupConLossV2 (sim_head/sim_loss.py:44-80).
+State-dict keys: roi_heads.model_sim.mlp.{0,2}.  The loss runs as the fused kernels of
+csrc/supcon.cu (forward and backward), fed by a row-id list into [F ; E] instead of a concatenated
+bank."""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from .. import capi
+
+
+class Sim_Net(nn.Module):
+    def __init__(self, config, in_dim):
+        super().__init__()
+        self.mlp = nn.Sequential(nn.Linear(in_dim, in_dim), nn.ReLU(inplace=True), nn.Linear(in_dim, 128))
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+                nn.init.constant_(m.bias, 0)
+
+    def forward(self, roi_feat):
+        return F.normalize(self.mlp(roi_feat), dim=1)
+
+
+class _SupConBankFn(Function):
+    """loss = mean_r( -log(pos_r / all_r) * w_r ) over the bank rows V[row_src], V = [Fm ; E]."""
+
+    @staticmethod
+    def forward(ctx, Fm, E, row_src, row_lab, row_w, M_dev, Mcap, inv_temp):
+        Fm, E = Fm.contiguous(), E.contiguous()
+        loss, stats = capi.supcon_forward(Fm, E, row_src, row_lab, row_w, M_dev, Mcap, inv_temp)
+        ctx.save_for_backward(Fm, E, row_src, row_lab, row_w, M_dev, stats)
+        ctx.Mcap, ctx.inv_temp = Mcap, inv_temp
+        return loss.view(())
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        Fm, E, row_src, row_lab, row_w, M_dev, stats = ctx.saved_tensors
+        g = g.contiguous().view(1).float()
+        dF, dE = capi.supcon_backward(Fm, E, row_src, row_lab, row_w, M_dev, ctx.Mcap, ctx.inv_temp, stats, g)
+        return dF, dE, None, None, None, None, None, None
+
+
+def supcon_bank_loss(Fm, E, row_src, row_lab, row_w, M_dev, Mcap, temperature):
+    return _SupConBankFn.apply(Fm, E, row_src, row_lab, row_w, M_dev, Mcap, 1.0 / temperature)
+
+
+class SupConLossV2(nn.Module):
+    """Drop-in for sim_loss.py:44-80: forward(overlaps_enc: list of [n_c,128] per class, score_col, device)."""
+
+    def __init__(self, temperature=0.2):
+        super().__init__()
+        self.temperature = temperature
+
+    def forward(self, overlaps_enc, score_col, device=None):
+        feats, labs = [], []
+        for i, e in enumerate(overlaps_enc):
+            if e.shape[0] != 0:
+                feats.append(e)
+                labs.append(torch.full((e.shape[0],), i, dtype=torch.int32, device=e.device))
+        feats, labs = torch.cat(feats), torch.cat(labs)
+        M = feats.shape[0]
+        src = torch.arange(M, dtype=torch.int32, device=feats.device)
+        M_dev = torch.full((1,), M, dtype=torch.int32, device=feats.device)
+        E = feats.new_zeros((1, 128))
+        return supcon_bank_loss(feats, E, src, labs, score_col.detach().float().contiguous(), M_dev, M,
+                                self.temperature)

@@ -1,0 +1,115 @@
+"""VGG16-OICR conv body and the VGG16.roi_head feature extractor (modeling/backbone/vgg16.py).
+Module tree and state-dict keys are the reference's: backbone.body.features.{0..28},
+roi_heads.feature_extractor.classifier.{1,4}."""
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+
+from . import registry
+from .dropblock import DropBlock2D
+from .poolers import Pooler
+
+
+class Identity(nn.Module):
+    def __init__(self, *args, **kwargs):
+        super().__init__()
+
+    def forward(self, x):
+        return x
+
+
+vgg_cfg = {
+    "VGG16-OICR": [64, 64, "M", 128, 128, "M", 256, 256, 256, "M", 512, 512, 512, "I", "512-D", "512-D", "512-D"],
+}
+
+
+def make_layers(cfg_list):
+    """vgg16.py:58-83: 13 convs, 3 max-pools, pool4 removed ('I'), conv5 dilation 2, last ReLU dropped."""
+    layers, in_ch = [], 3
+    for v in cfg_list:
+        if v == "M":
+            layers.append(nn.MaxPool2d(kernel_size=2, stride=2))
+        elif v == "I":
+            layers.append(Identity())
+        elif isinstance(v, str) and "-D" in v:
+            c = int(v.split("-")[0])
+            layers += [nn.Conv2d(in_ch, c, kernel_size=3, padding=2, dilation=2), nn.ReLU(inplace=True)]
+            in_ch = c
+        else:
+            layers += [nn.Conv2d(in_ch, v, kernel_size=3, padding=1), nn.ReLU(inplace=True)]
+            in_ch = v
+    return nn.Sequential(*layers[:-1])
+
+
+class VGG_Base(nn.Module):
+    def __init__(self, features, cfg, init_weights=True):
+        super().__init__()
+        self.features = features
+        if init_weights:
+            for m in self.modules():
+                if isinstance(m, nn.Conv2d):
+                    nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+                    nn.init.constant_(m.bias, 0)
+        freeze_at = cfg.MODEL.BACKBONE.FREEZE_CONV_BODY_AT           # vgg16.py:48-55
+        if freeze_at >= 0:
+            for layer in range([5, 10, 17, 23, 29][freeze_at - 1]):
+                for p in self.features[layer].parameters():
+                    p.requires_grad = False
+
+    def forward(self, x):
+        return [self.features(x)]
+
+
+@registry.BACKBONES.register("VGG16-OICR")
+def add_conv_body(cfg, dim_in=3):
+    body = VGG_Base(make_layers(vgg_cfg[cfg.MODEL.BACKBONE.CONV_BODY]), cfg)
+    model = nn.Sequential(OrderedDict([("body", body)]))
+    model.out_channels = 512
+    return model
+
+
+@registry.ROI_BOX_FEATURE_EXTRACTORS.register("VGG16.roi_head")
+class VGG16FC67ROIFeatureExtractor(nn.Module):
+    def __init__(self, config, in_channels, init_weights=True):
+        super().__init__()
+        assert in_channels == 512
+        res = config.MODEL.ROI_BOX_HEAD.POOLER_RESOLUTION
+        self.pooler = Pooler(output_size=(res, res), scales=config.MODEL.ROI_BOX_HEAD.POOLER_SCALES,
+                             sampling_ratio=config.MODEL.ROI_BOX_HEAD.POOLER_SAMPLING_RATIO)
+        self.classifier = nn.Sequential(Identity(), nn.Linear(512 * 7 * 7, 4096), nn.ReLU(inplace=True),
+                                        nn.Dropout(), nn.Linear(4096, 4096), nn.ReLU(inplace=True), nn.Dropout())
+        self.out_channels = 4096
+        if config.DB.METHOD == "dropblock":
+            self.dropblock = DropBlock2D(block_size=3, drop_prob=0.3)
+        self.sim_drop = DropBlock2D(block_size=1, drop_prob=0.3)
+        self.noise_sampler = None      # test hook: callable(shape, device) -> N(0,1) tensor
+        if init_weights:
+            for m in self.modules():
+                if isinstance(m, nn.Linear):
+                    nn.init.normal_(m.weight, 0, 0.01)
+                    nn.init.constant_(m.bias, 0)
+
+    def forward(self, x, proposals):                     # vgg16.py:148-153
+        pooled_feat = self.pooler(x, proposals)
+        x = self.classifier(pooled_feat.view(pooled_feat.shape[0], -1))
+        return x, pooled_feat
+
+    def forward_pooler(self, x, proposals):
+        return self.pooler(x, proposals)
+
+    def forward_neck(self, x):                           # vgg16.py:159-162
+        return self.classifier(x.view(x.shape[0], -1))
+
+    def forward_dropblock(self, pooled_feats, proposals):  # vgg16.py:165-167
+        return self.dropblock(pooled_feats)
+
+    def drop_pool(self, pooled_feats):                   # vgg16.py:173-175
+        return self.sim_drop(pooled_feats)
+
+    def noise_pool(self, pooled_feats):                  # vgg16.py:177-180
+        if self.noise_sampler is not None:
+            noise = self.noise_sampler(pooled_feats.shape, pooled_feats.device)
+        else:
+            noise = torch.randn(pooled_feats.shape, device=pooled_feats.device)
+        return noise * pooled_feats + pooled_feats

@@ -1,0 +1,51 @@
+"""ROIWeakRegHead (roi_heads/weak_head/weak_head.py:72-157): feature extract -> Sim_Net ->
+DropBlock aug -> MISTPredictor -> RoIRegLoss.  Attribute names (feature_extractor, predictor,
+model_sim, loss_evaluator) and the return tuple are the reference's."""
+import torch
+from torch import nn
+
+from . import registry
+from .loss import make_roi_weak_loss_evaluator
+from .sim_head import Sim_Net
+from . import predictors, vgg16  # noqa: F401  (registers the builders)
+
+
+class ROIWeakRegHead(nn.Module):
+    def __init__(self, cfg, in_channels):
+        super().__init__()
+        self.feature_extractor = registry.ROI_BOX_FEATURE_EXTRACTORS[cfg.MODEL.ROI_BOX_HEAD.FEATURE_EXTRACTOR](cfg, in_channels)
+        self.predictor = registry.ROI_WEAK_PREDICTOR[cfg.MODEL.ROI_WEAK_HEAD.PREDICTOR](cfg, self.feature_extractor.out_channels)
+        self.loss_evaluator = make_roi_weak_loss_evaluator(cfg)
+        self.HEUR = cfg.MODEL.ROI_WEAK_HEAD.REGRESS_HEUR
+        self.DB_METHOD = cfg.DB.METHOD
+        self.model_sim = Sim_Net(cfg, self.feature_extractor.out_channels)
+
+    def go_through_cdb(self, features, proposals, model_cdb):              # weak_head.py:87-99
+        if not self.training or self.DB_METHOD == "none":
+            return features
+        if self.DB_METHOD == "dropblock":
+            return self.feature_extractor.forward_dropblock(features, proposals)
+        raise ValueError("DB.METHOD %r is outside the hot path (every shipped config uses 'dropblock')" % self.DB_METHOD)
+
+    def forward(self, features, proposals, targets=None, model_cdb=None, iteration=None):
+        clean_roi_feats, clean_pooled_feats = self.feature_extractor.forward(features, proposals)     # :107
+        if not self.training:
+            cls_score, det_score, ref_scores, ref_bbox_preds = self.predictor(clean_roi_feats, proposals)
+            # test-time post-processing (box_head/inference.py) is SURVEY row N4 ("next"): return raw scores
+            final_score = torch.mean(torch.stack(ref_scores), dim=0)
+            final_regression = torch.mean(torch.stack(ref_bbox_preds), dim=0)
+            return clean_roi_feats, (final_score, final_regression), {}, {}
+        sim_feature = self.model_sim(clean_roi_feats)                                                 # :110
+        aug_pooled_feats = self.go_through_cdb(clean_pooled_feats, proposals, model_cdb)              # :111
+        aug_roi_feats = self.feature_extractor.forward_neck(aug_pooled_feats)                         # :112
+        cls_score, det_score, ref_scores, ref_bbox_preds = self.predictor(aug_roi_feats, proposals)   # :113
+        loss_img, accuracy_img = self.loss_evaluator([cls_score], [det_score], ref_scores, ref_bbox_preds,
+                                                     sim_feature, clean_pooled_feats, self.feature_extractor,
+                                                     self.model_sim, proposals, targets)              # :120
+        return aug_roi_feats, proposals, loss_img, accuracy_img
+
+
+def build_roi_weak_head(cfg, in_channels):
+    if not cfg.MODEL.ROI_WEAK_HEAD.REGRESS_ON:
+        raise NotImplementedError("ROIWeakHead (no regression) is not selected by any shipped config")
+    return ROIWeakRegHead(cfg, in_channels)

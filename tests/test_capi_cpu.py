@@ -1,0 +1,95 @@
+"""CPU-only checks of the drop-in boundary and the host logic: the C-ABI library loads and exports
+every symbol include/odwscl.h declares (no compute calls without a GPU); the host-side mirror has
+the reference's operator surface (names, state-dict keys, parameter count)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "odwscl.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(odwscl_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from odwscl_b200 import capi
+    L = ctypes.CDLL(capi.LIB_PATH)
+    syms = header_symbols()
+    assert len(syms) >= 18
+    for s in syms:
+        assert hasattr(L, s), "missing export: " + s
+    assert set(syms) == set(capi.EXPORTS), set(syms) ^ set(capi.EXPORTS)
+    assert capi.lib().odwscl_version() == 100
+    assert capi.lib().odwscl_strerror(-1) == b"odwscl: invalid argument"
+
+
+def test_product_path_never_imports_oracle():
+    pkg = os.path.join(ROOT, "od-wscl_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "oracle" not in txt.replace("# oracle", ""), os.path.join(dp, f)
+
+
+def test_cpu_tensors_fail_loudly():
+    from odwscl_b200 import _C, capi
+    with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
+        _C.roi_pool_forward(torch.zeros(1, 4, 5, 5), torch.zeros(1, 5), 0.125, 7, 7)
+    with pytest.raises(RuntimeError):
+        capi.box_iou(torch.zeros(2, 4), torch.zeros(2, 4))
+    for n in ("deform_conv_forward", "sigmoid_focalloss_forward", "deform_psroi_pooling_backward"):
+        with pytest.raises(RuntimeError, match="outside the proposal-feature hot path"):
+            getattr(_C, n)()
+
+
+def test_model_surface_matches_reference():
+    from odwscl_b200.config import cfg
+    from odwscl_b200.modeling import build_detection_model, registry
+    from oracle import oracle as orc
+    for reg, key in ((registry.BACKBONES, "VGG16-OICR"), (registry.ROI_BOX_FEATURE_EXTRACTORS, "VGG16.roi_head"),
+                     (registry.ROI_WEAK_PREDICTOR, "MISTPredictor"), (registry.ROI_WEAK_LOSS, "RoIRegLoss")):
+        assert key in reg
+    m = build_detection_model(cfg)
+    assert m.backbone.out_channels == 512
+    assert sum(p.numel() for p in m.parameters()) == 153028901
+    sd = orc.synth_state_dict(21, 0)
+    assert set(sd) == set(m.state_dict())
+    frozen = [n for n, p in m.named_parameters() if not p.requires_grad]
+    assert frozen == ["backbone.body.features.%d.%s" % (i, s) for i in (0, 2, 5, 7) for s in ("weight", "bias")]
+
+
+def test_boxlist_and_image_list():
+    from odwscl_b200.structures import BoxList, to_image_list
+    b = BoxList(torch.tensor([[0., 0., 9., 9.], [2., 3., 5., 7.]]), (10, 10))
+    assert b.area().tolist() == [100.0, 20.0]
+    assert b.convert("xywh").bbox.tolist() == [[0, 0, 10, 10], [2, 3, 4, 5]]
+    assert torch.equal(b.convert("xywh").convert("xyxy").bbox, b.bbox)
+    il = to_image_list([torch.ones(3, 600, 1000), torch.ones(3, 500, 900)], 32)
+    assert tuple(il.tensors.shape) == (2, 3, 608, 1024)
+    assert float(il.tensors[1, :, 500:].sum()) == 0.0
+
+
+def test_wetectron_shim_installs_C():
+    import sys
+    from odwscl_b200 import wetectron_shim
+    saved = {k: sys.modules.get(k) for k in ("wetectron", "wetectron._C", "wetectron.layers")}
+    try:
+        for k in saved:
+            sys.modules.pop(k, None)
+        pkg = wetectron_shim.install()
+        from wetectron import _C
+        assert _C.roi_pool_forward.__module__.endswith("_C")
+        from wetectron.layers import ROIPool
+        assert repr(ROIPool((7, 7), 0.125)) == "ROIPool(output_size=(7, 7), spatial_scale=0.125)"
+    finally:
+        for k, v in saved.items():
+            sys.modules.pop(k, None)
+            if v is not None:
+                sys.modules[k] = v

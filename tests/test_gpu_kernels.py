@@ -1,0 +1,216 @@
+"""GPU parity tests proper: the sm_100a kernels, called through the C ABI (odwscl_b200.capi ->
+libodwscl_sm100.so), against the CPU oracle (oracle/) and the reference-generated golden vectors
+(tests/golden/).  Bit-exact for index / selection work; stated tolerances for floating point."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from odwscl_b200 import capi as c
+    c.lib()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return c
+
+
+def cu(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+# ------------------------------------------------------------------------------- ROIPool
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_roi_pool_golden(capi, golden, tag):
+    G = golden("roi_pool.npz")
+    ph, pw = [int(x) for x in G[tag + "_pooled"]]
+    out, arg = capi.roi_pool_forward(cu(G[tag + "_feat"]), cu(G[tag + "_rois"]), 0.125, ph, pw)
+    assert np.array_equal(out.cpu().numpy(), G[tag + "_out"])
+    assert np.array_equal(arg.cpu().numpy(), G[tag + "_argmax"])
+    B, C, H, W = G[tag + "_feat"].shape
+    gi = capi.roi_pool_backward(cu(G[tag + "_grad_out"]), cu(G[tag + "_rois"]), arg, ph, pw, B, C, H, W)
+    np.testing.assert_allclose(gi.cpu().numpy(), G[tag + "_grad_in"], rtol=1e-5, atol=1e-5)
+
+
+def _rand_rois(g, B, H, W, n, scale=0.125, wild=True):
+    iw, ih = W / scale, H / scale
+    x1 = torch.rand(n, generator=g) * iw * (1.2 if wild else 0.9) - (0.1 * iw if wild else 0)
+    y1 = torch.rand(n, generator=g) * ih * (1.2 if wild else 0.9) - (0.1 * ih if wild else 0)
+    w = torch.rand(n, generator=g) * iw * 0.8 - (0.05 * iw if wild else 0)
+    h = torch.rand(n, generator=g) * ih * 0.8 - (0.05 * ih if wild else 0)
+    b = torch.randint(0, B, (n,), generator=g).float()
+    return torch.stack([b, x1, y1, x1 + w, y1 + h], 1)
+
+
+@pytest.mark.parametrize("B,C,H,W,R,quant", [(2, 8, 19, 27, 64, False), (1, 128, 38, 50, 97, True),
+                                             (2, 132, 20, 31, 50, False), (1, 512, 12, 17, 33, True)])
+def test_roi_pool_fast_path_vs_oracle(capi, B, C, H, W, R, quant):
+    """7x7, C % 4 == 0 -> channels-last warp-per-bin-row kernel; bit-exact incl. ties / empty bins."""
+    g = torch.Generator().manual_seed(B * 1000 + C)
+    feat = torch.randn(B, C, H, W, generator=g)
+    if quant:
+        feat = (feat * 2).round() / 2
+    rois = _rand_rois(g, B, H, W, R)
+    eo, ea = orc.roi_pool_forward(feat.numpy(), rois.numpy(), 0.125, 7, 7)
+    out, arg = capi.roi_pool_forward(feat.cuda(), rois.cuda(), 0.125, 7, 7)
+    assert np.array_equal(out.cpu().numpy(), eo)
+    assert np.array_equal(arg.cpu().numpy(), ea)
+    go = torch.randn(out.shape, generator=g)
+    gi = capi.roi_pool_backward(go.cuda(), rois.cuda(), arg, 7, 7, B, C, H, W)
+    egi = orc.roi_pool_backward(go.numpy(), ea, rois.numpy(), B, C, H, W)
+    np.testing.assert_allclose(gi.cpu().numpy(), egi, rtol=1e-4, atol=1e-4)
+
+
+def test_roi_pool_empty_and_errors(capi):
+    feat = torch.randn(1, 8, 5, 5).cuda()
+    out, arg = capi.roi_pool_forward(feat, torch.zeros((0, 5)).cuda(), 0.125, 7, 7)
+    assert out.shape == (0, 8, 7, 7) and arg.shape == (0, 8, 7, 7)
+    gi = capi.roi_pool_backward(out, torch.zeros((0, 5)).cuda(), arg, 7, 7, 1, 8, 5, 5)
+    assert float(gi.abs().sum()) == 0.0
+    from odwscl_b200 import _C
+    with pytest.raises(RuntimeError, match="Not implemented on the CPU"):      # csrc/ROIPool.h:23
+        _C.roi_pool_forward(feat.cpu(), torch.zeros((1, 5)), 0.125, 7, 7)
+
+
+def test_roi_pool_full_size_properties(capi):
+    """BASELINE configs[1] shape: 2 x 512 x 76 x 128 map, 2000 rois / image.  Size-independent
+    properties: out == feat[argmax]; argmax inside the roi's clipped extent; backward conserves
+    mass; agreement with torchvision's kernel (same Caffe2 lineage) on the GPU."""
+    import torchvision
+    B, C, H, W, N = 2, 512, 76, 128, 2000
+    g = torch.Generator().manual_seed(5)
+    feat = torch.randn(B, C, H, W, generator=g).cuda()
+    rois = torch.cat([torch.cat([torch.full((N, 1), float(b)), orc.synth_boxes(N, 1000, 600, g)], 1)
+                      for b in range(B)]).cuda()
+    out, arg = capi.roi_pool_forward(feat, rois, 0.125, 7, 7)
+    tv_out, tv_arg = torch.ops.torchvision.roi_pool(feat, rois, 0.125, 7, 7)
+    assert torch.equal(out, tv_out)
+    assert torch.equal(arg, tv_arg.int())
+    bidx = rois[:, 0].long()
+    planes = feat.view(B, C, H * W)[bidx]                       # [R,C,HW]
+    valid = arg >= 0
+    gathered = torch.gather(planes, 2, arg.clamp(min=0).long().view(B * N, C, 49)).view_as(out)
+    assert torch.equal(gathered[valid], out[valid])
+    assert float(out[~valid].abs().sum()) == 0.0
+    go = torch.randn(out.shape, generator=torch.Generator(device="cuda").manual_seed(1), device="cuda")
+    gi = capi.roi_pool_backward(go, rois, arg, 7, 7, B, C, H, W)
+    tot_in, tot_out = float(gi.double().sum()), float((go * valid).double().sum())
+    assert abs(tot_in - tot_out) <= 1e-3 * max(1.0, abs(tot_out))
+    # linearity of the backward in grad_out
+    gi2 = capi.roi_pool_backward(2.0 * go, rois, arg, 7, 7, B, C, H, W)
+    torch.testing.assert_close(gi2, 2.0 * gi, rtol=1e-4, atol=1e-3)
+
+
+# ------------------------------------------------------------------------------- ROIAlign
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_roi_align_golden(capi, golden, tag):
+    G = golden("roi_align.npz")
+    sr = int(G[tag + "_sr"])
+    out = capi.roi_align_forward(cu(G[tag + "_feat"]), cu(G[tag + "_rois"]), 0.125, 7, 7, sr)
+    np.testing.assert_allclose(out.cpu().numpy(), G[tag + "_out"], rtol=1e-5, atol=1e-5)
+    B, C, H, W = G[tag + "_feat"].shape
+    gi = capi.roi_align_backward(cu(G[tag + "_grad_out"]), cu(G[tag + "_rois"]), 0.125, 7, 7, B, C, H, W, sr)
+    np.testing.assert_allclose(gi.cpu().numpy(), G[tag + "_grad_in"], rtol=1e-4, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------- IoU / NMS
+def test_iou_nms_golden(capi, golden):
+    G = golden("boxes.npz")
+    P, Q, S = cu(G["P"]), cu(G["Q"]), cu(G["scores"])
+    assert np.array_equal(capi.box_iou(P, Q, True).cpu().numpy(), G["iou"])
+    assert np.array_equal(capi.nms(P, S, 0.3).cpu().numpy(), G["tv_nms_full"])
+    cl = torch.from_numpy(G["cluster"]).cuda()
+    for t in range(3):
+        thr = float(G["easy_nms_thr_%d" % t])
+        keep = cl[capi.nms(P[cl], S[cl], thr)]
+        assert np.array_equal(keep.cpu().numpy(), G["easy_nms_%d" % t])
+    # legacy `_C.nms`: CUDA rule is '>' (csrc/cuda/nms.cu:60); compare with the oracle's ge=False
+    Su = cu(G["scores_u"])
+    for thr in (0.1, 0.3, 0.7):
+        assert np.array_equal(capi.nms_legacy(P, Su, thr).cpu().numpy(), orc.nms_legacy(G["P"], G["scores_u"], thr, ge=False))
+
+
+@pytest.mark.parametrize("n,ties", [(1, False), (31, True), (700, True), (2000, False), (4000, True)])
+def test_nms_random_vs_oracle(capi, n, ties):
+    g = torch.Generator().manual_seed(n)
+    P = orc.synth_boxes(n, 1000, 600, g)
+    if n > 40:
+        P[n // 2: n // 2 + 10] = P[:10]                       # exact duplicates
+    s = torch.rand(n, generator=g)
+    if ties:
+        s = (s * 16).round() / 16
+    for thr in (0.1, 0.5):
+        got = capi.nms(P.cuda(), s.cuda(), thr).cpu().numpy()
+        assert np.array_equal(got, orc.nms_tv(P.numpy(), s.numpy(), thr))
+    assert np.array_equal(capi.box_iou(P.cuda(), P[:7].cuda(), False).cpu().numpy(),
+                          orc.box_iou(P.numpy(), P[:7].numpy(), False))
+
+
+def test_nms_empty(capi):
+    assert capi.nms(torch.zeros((0, 4)).cuda(), torch.zeros((0,)).cuda(), 0.5).numel() == 0
+
+
+# ------------------------------------------------------------------------------- SupCon
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_supcon_golden(capi, golden, tag):
+    """fp32 loss within 1e-4 rel (north_star tolerance), gradient within 2e-4 rel."""
+    from odwscl_b200.modeling.sim_head import supcon_bank_loss
+    G = golden("supcon.npz")
+    f = cu(G[tag + "_feats"]).requires_grad_(True)
+    M = f.shape[0]
+    src = torch.arange(M, dtype=torch.int32, device="cuda")
+    lab = cu(G[tag + "_labels"]).to(torch.int32)
+    loss = supcon_bank_loss(f, f.new_zeros((1, 128)), src, lab, cu(G[tag + "_w"]),
+                            torch.full((1,), M, dtype=torch.int32, device="cuda"), M + 37, 0.2)
+    loss.backward()
+    ref = float(G[tag + "_loss"])
+    assert abs(float(loss) - ref) <= 1e-4 * abs(ref)
+    np.testing.assert_allclose(f.grad.cpu().numpy(), G[tag + "_grad"], rtol=2e-3, atol=2e-8)
+
+
+def test_supcon_module_duplicates(capi):
+    """bank rows that repeat a source row (the [m] fallback, loss.py:338) accumulate their grads."""
+    from odwscl_b200.modeling.sim_head import supcon_bank_loss
+    g = torch.Generator().manual_seed(3)
+    Fm = torch.nn.functional.normalize(torch.randn(50, 128, generator=g), dim=1)
+    E = torch.nn.functional.normalize(torch.randn(20, 128, generator=g), dim=1)
+    src = torch.randint(0, 70, (90,), generator=g)
+    lab = torch.randint(0, 3, (90,), generator=g)
+    w = torch.rand(90, generator=g)
+    Fc, Ec = Fm.clone().requires_grad_(True), E.clone().requires_grad_(True)
+    bank = torch.cat([Fc, Ec])[src]
+    ref = orc.supcon_v2(bank, lab.float(), w, 0.2)
+    ref.backward()
+    Fg, Eg = Fm.cuda().requires_grad_(True), E.cuda().requires_grad_(True)
+    loss = supcon_bank_loss(Fg, Eg, src.int().cuda(), lab.int().cuda(), w.cuda(),
+                            torch.full((1,), 90, dtype=torch.int32, device="cuda"), 128, 0.2)
+    loss.backward()
+    assert abs(float(loss) - float(ref)) <= 1e-4 * abs(float(ref))
+    np.testing.assert_allclose(Fg.grad.cpu().numpy(), Fc.grad.numpy(), rtol=2e-3, atol=1e-7)
+    np.testing.assert_allclose(Eg.grad.cpu().numpy(), Ec.grad.numpy(), rtol=2e-3, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------- DropBlock / sim
+@pytest.mark.parametrize("block", [1, 3])
+def test_dropblock_vs_oracle(capi, block):
+    g = torch.Generator().manual_seed(block)
+    x = torch.randn(37, 12, 7, 7, generator=g)
+    cen = (torch.rand(37, 7, 7, generator=g) < 0.3 / block ** 2).float()
+    y, sc = capi.dropblock(x.cuda(), cen.cuda(), block)
+    np.testing.assert_allclose(y.cpu().numpy(), orc.dropblock(x, cen, block).numpy(), rtol=1e-6, atol=1e-7)
+    gy, _ = capi.dropblock(x.cuda(), cen.cuda(), block, sc)          # backward re-uses the stored scale
+    assert torch.equal(gy, y)
+
+
+def test_sim_nxn(capi):
+    g = torch.Generator().manual_seed(0)
+    Fm = torch.nn.functional.normalize(torch.randn(333, 128, generator=g), dim=1)
+    got = capi.sim_nxn(Fm.cuda()).cpu()
+    torch.testing.assert_close(got, Fm @ Fm.T, rtol=1e-5, atol=1e-6)

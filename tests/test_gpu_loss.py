@@ -1,0 +1,204 @@
+"""GPU parity of the contrastive head (object discovery + SupCon + od_layer + MIL/refine losses)
+against the reference-generated golden vectors and the oracle, and of the full model at
+BASELINE.json configs[0]."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import oracle as orc
+from tests.helpers import case_tensors, grid_sim
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def strict_fp32():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+
+
+class CpuStandInExtractor:
+    """The tiny stand-in of tests/golden/roi_reg_loss.npz.  It computes on the CPU exactly as the
+    fixture generator did, so the embeddings fed to the GPU kernels are bit-identical to the
+    reference run; what is under test is everything the product does with them."""
+
+    def __init__(self, t, rng):
+        self.t, self.rng = t, rng
+
+    def drop_pool(self, x):
+        x = x.cpu()
+        return orc.dropblock(x, self.rng.dropblock_centres(x.shape[0], 1), 1)
+
+    def noise_pool(self, x):
+        x = x.cpu()
+        return self.rng.noise(x.shape) * x + x
+
+    def forward_neck(self, x):
+        return torch.relu(F.linear(x.reshape(x.shape[0], -1), self.t["fe_w"], self.t["fe_b"]))
+
+
+def product_loss_case(G, tag):
+    from odwscl_b200.config import cfg
+    from odwscl_b200.modeling.loss import RoIRegLossComputation
+    from odwscl_b200.structures import BoxList
+    t = case_tensors(G, tag)          # CPU leaf tensors
+    dev = {k: t[k].detach().cuda().requires_grad_(True) for k in
+           ("cls", "det", "simf", "pooled", "ref0", "ref1", "ref2", "bb0", "bb1", "bb2")}
+    rng = orc.StochasticSource(t["seed"])
+    fe = CpuStandInExtractor(t, rng)
+    model_sim = lambda h: grid_sim(h, t["ms_w"], t["ms_b"]).cuda()
+    props = [BoxList(b.cuda(), (500, 375), "xyxy") for b in t["boxes"]]
+    targets = []
+    for lab in t["labels"]:
+        tg = BoxList(torch.zeros((len(lab), 4)), (500, 375), "xyxy")
+        tg.add_field("labels", torch.as_tensor(lab))
+        targets.append(tg)
+    ev = RoIRegLossComputation(cfg)
+    ev.batch_aug = False              # per-(image, class) drop/noise order, to replay the reference RNG
+    losses, accs = ev([dev["cls"]], [dev["det"]], [dev["ref0"], dev["ref1"], dev["ref2"]],
+                      [dev["bb0"], dev["bb1"], dev["bb2"]], dev["simf"], dev["pooled"], fe, model_sim, props, targets)
+    return t, dev, ev, losses, accs
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_roi_reg_loss_golden(golden, tag):
+    """Index selection bit-exact (discovered instances, pseudo labels); losses <= 1e-4 rel
+    (north_star); gradients within 2e-3 rel of the reference's autograd."""
+    G = golden("roi_reg_loss.npz")
+    t, dev, ev, losses, accs = product_loss_case(G, tag)
+    st = ev.last_state
+    pair_img, pair_cls = st.pair_img.cpu().numpy(), st.pair_cls.cpu().numpy()
+    inst, cnt = st.inst.cpu().numpy(), st.inst_cnt.cpu().numpy()
+    seen = set()
+    for p in range(st.P):
+        for i in range(3):
+            key = "%s_inst_%d_%d_%d" % (tag, pair_img[p], i, pair_cls[p])
+            seen.add(key)
+            assert np.array_equal(inst[p, i, :cnt[p, i]], G[key]), key
+    assert seen == {k for k in G if k.startswith(tag + "_inst_")}
+    from odwscl_b200 import capi
+    pl, lw, rt = capi.od_layer(st, 0.5)
+    off = 0
+    for b, n in enumerate(t["sizes"]):
+        for i in range(3):
+            assert np.array_equal(pl[i, off:off + n].cpu().numpy(), G["%s_pl_%d_%d" % (tag, b, i)])
+            np.testing.assert_allclose(lw[i, off:off + n].cpu().numpy(), G["%s_lw_%d_%d" % (tag, b, i)], rtol=1e-5)
+            np.testing.assert_allclose(rt[i, off:off + n].cpu().numpy(), G["%s_rt_%d_%d" % (tag, b, i)],
+                                       rtol=1e-5, atol=1e-6)
+        off += n
+    for k, v in losses.items():
+        ref = float(G["%s_loss_%s" % (tag, k)])
+        assert abs(float(v) - ref) <= 1e-4 * abs(ref) + 1e-9, (k, float(v), ref)
+    for k, v in accs.items():
+        assert abs(float(v) - float(G["%s_acc_%s" % (tag, k)])) <= 1e-6, k
+    sum(losses.values()).backward()
+    for k in ("cls", "det", "simf", "pooled", "ref0", "ref1", "ref2", "bb0", "bb1", "bb2"):
+        np.testing.assert_allclose(dev[k].grad.cpu().numpy(), G["%s_g_%s" % (tag, k)], rtol=2e-3, atol=2e-8,
+                                   err_msg=k)
+
+
+def test_discovery_stagewise_vs_oracle_random():
+    """Larger random case on the exact similarity grid (N = 1500 / 1100, 3 + 2 classes): every
+    discovered set, bank row order and weight order equals the oracle's, bit for bit."""
+    from odwscl_b200 import capi
+    from oracle.gen_golden import grid_features
+    g = torch.Generator().manual_seed(21)
+    sizes, C = [1500, 1100], 21
+    pos = [[2, 9, 17], [5, 9]]
+    R = sum(sizes)
+    boxes = [orc.synth_boxes(n, 1000, 600, g) for n in sizes]
+    mk = lambda *s: torch.randn(*s, generator=g) * 2.0
+    final = torch.softmax(mk(R, C), 1) * torch.cat([torch.softmax(d, 0) for d in mk(R, C).split(sizes)])
+    refl = [mk(R, C) for _ in range(3)]
+    simf = grid_features(R, g)
+    emb = {}
+
+    def embed_aug(b, c, I, kind):
+        e = grid_features(len(I), torch.Generator().manual_seed(1000 * b + 10 * c + (kind == "drop")))
+        emb[(b, c, kind)] = e
+        return e
+    bank, Wt, inst, idx, tr = orc.discover(boxes, final.split(sizes), [r.split(sizes) for r in refl], simf.split(sizes),
+                                           pos, embed_aug, 0.5, 0.1, C)
+    ofeat, olab = [], []
+    for c, rows in enumerate(bank):
+        if rows:
+            ofeat.append(torch.cat(rows)); olab += [c] * ofeat[-1].shape[0]
+    ofeat, ow = torch.cat(ofeat), torch.cat([w.view(-1) for w in Wt])
+
+    pair_img = [b for b in range(2) for _ in pos[b]]
+    pair_cls = [c for b in range(2) for c in pos[b]]
+    P = len(pair_img)
+    i32 = lambda x: torch.tensor(x, dtype=torch.int32).cuda()
+    scores = (final.cuda().contiguous(), torch.softmax(refl[0], 1).cuda().contiguous(),
+              torch.softmax(refl[1], 1).cuda().contiguous())
+    st = capi.discover_phase_a(torch.cat(boxes).cuda(), i32([0, sizes[0], R]), scores, i32(pair_img), i32(pair_cls),
+                               max(sizes), 0.5)
+    offA = st.offA.cpu().numpy()
+    K = int(offA[P])
+    rowsA = st.rowsA[:K].cpu().numpy()
+    img_off = [0, sizes[0]]
+    for p in range(P):
+        exp = tr["phaseA_idx"][(pair_img[p], pair_cls[p])] + img_off[pair_img[p]]
+        assert np.array_equal(rowsA[offA[p]:offA[p + 1]], exp)
+    E = torch.cat([emb[(pair_img[p], pair_cls[p], "drop")] for p in range(P)] +
+                  [emb[(pair_img[p], pair_cls[p], "noise")] for p in range(P)]).cuda()
+    capi.discover_phase_b(st, simf.cuda(), E, 0.1)
+    capi.bank_assemble(st, C - 1, 3 * K + 3 * sum(sizes[b] for b in pair_img))
+    M = int(st.M.item())
+    instd, cnt = st.inst.cpu().numpy(), st.inst_cnt.cpu().numpy()
+    tau = st.tau.cpu().numpy()
+    for p in range(P):
+        for i in range(3):
+            key = (pair_img[p], i, pair_cls[p])
+            assert tau[p, i] == np.float32(tr["tau"][key]), key
+            assert np.array_equal(instd[p, i, :cnt[p, i]], inst[key[0]][i][key[2]]), key
+    assert M == ofeat.shape[0]
+    V = torch.cat([simf, E.cpu()])
+    assert torch.equal(V[st.row_src[:M].cpu().long()], ofeat)
+    assert st.row_lab[:M].cpu().tolist() == olab
+    np.testing.assert_allclose(st.row_w[:M].cpu().numpy(), ow.numpy(), rtol=2e-6)
+
+
+def test_model_cfg1_golden(golden):
+    """BASELINE.json configs[0] (1 x 600x600, 256 proposals, VGG16 random init): the product
+    GeneralizedRCNN on the GPU (strict fp32) against the reference's losses.  ROI features within
+    1e-4 rel; losses within 1e-3 rel (13 conv layers of cuDNN-vs-MKL rounding in between);
+    loss_sim is compared on its own."""
+    from odwscl_b200.config import cfg
+    from odwscl_b200.modeling import build_detection_model
+    from odwscl_b200.structures import BoxList
+    G = golden("model_cfg1.npz")
+    model = build_detection_model(cfg)
+    model.load_state_dict(orc.synth_state_dict(21, seed=0), strict=True)
+    model.cuda().train()
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    images, boxes, labels = orc.synth_batch(1, 256, 600, 600, 21, seed=1234)
+    rng = orc.StochasticSource(4242)
+    fe = model.roi_heads.feature_extractor
+    sampler = lambda n, h, w, gamma, dev: (torch.rand(n, h, w, generator=rng.g) < gamma).float().to(dev)
+    fe.dropblock.centre_sampler = sampler
+    fe.sim_drop.centre_sampler = sampler
+    fe.noise_sampler = lambda shape, dev: rng.noise(tuple(shape)).to(dev)
+    model.roi_heads.loss_evaluator.batch_aug = False
+    with torch.no_grad():
+        feat = model.backbone(images.cuda())[0]
+    ref_s = torch.from_numpy(G["feat_sample"])
+    got_s = feat[0, ::37, ::5, ::7].cpu()
+    assert float((got_s - ref_s).abs().max()) <= 1e-4 * float(ref_s.abs().max())
+    props = [BoxList(b.cuda(), (600, 600), "xyxy") for b in boxes]
+    targets = []
+    for lab in labels:
+        t = BoxList(torch.zeros((len(lab), 4)), (600, 600), "xyxy")
+        t.add_field("labels", torch.as_tensor(lab))
+        targets.append(t)
+    losses, accs = model(images.cuda(), targets, props)
+    for k, v in losses.items():
+        ref = float(G["loss_" + k])
+        assert abs(float(v) - ref) <= 1e-3 * abs(ref), (k, float(v), ref)
+    sum(losses.values()).backward()
+    gsum = sum(float(p.grad.abs().sum()) for p in model.parameters() if p.grad is not None)
+    assert np.isfinite(gsum) and gsum > 0
