@@ -1,0 +1,32 @@
+#!/bin/bash
+# One GPU-box visit: parity tests, smoke, bench, ncu launch list + full capture of the top kernel.
+# Usage (under gpurun): bash scripts/gpu_round.sh [tag] [stages]   stages: any of t,s,b,l,n (default all)
+TAG=${1:-r01}
+ST=${2:-tsbln}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+export PYTHONUNBUFFERED=1
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > $OUT/gpu.csv 2>&1
+python -c "import torch; print(torch.__version__, torch.cuda.get_device_name(0))" > $OUT/env.txt 2>&1
+if [[ $ST == *t* ]]; then
+  timeout 900 python -m pytest tests -m gpu -x -q -rA > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_gpu.log
+  tail -40 $OUT/pytest_gpu.log
+fi
+if [[ $ST == *s* ]]; then
+  timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; echo "smoke rc=$?" >> $OUT/smoke.log
+  tail -5 $OUT/smoke.log
+fi
+if [[ $ST == *b* ]]; then
+  timeout 900 python bench.py --steps 10 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?" >> $OUT/bench.err
+  cat $OUT/bench.json; tail -5 $OUT/bench.err
+fi
+if [[ $ST == *l* ]]; then
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $OUT/launches.csv \
+      python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $OUT/bench_under_ncu.log 2>&1
+  echo "launch list rc=$?"; wc -l $OUT/launches.csv
+fi
+if [[ $ST == *n* ]]; then
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"roi_pool_fwd_nhwc7|roi_pool_bwd|nchw_to_nhwc" -c 6 \
+      -o $OUT/prof_roipool -f python scripts/run_roipool_once.py > $OUT/ncu_full.log 2>&1
+  echo "ncu full rc=$?"; ls -la $OUT
+fi
