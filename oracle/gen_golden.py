@@ -311,11 +311,39 @@ def gen_model_cfg1():
         il = to_image_list([im[:, :600, :600] for im in images], 32)
         feats = {}
         h = model.backbone.register_forward_hook(lambda m, i, o: feats.__setitem__("feat", o[0].detach()))
-        losses, acc = model(il, targets, props)
-        h.remove()
+        # first Sim_Net call of the step = sim_feature of all proposals (weak_head.py:110)
+        h2 = model.roi_heads.model_sim.register_forward_hook(
+            lambda m, i, o: (feats.setdefault("simf", o.detach().clone()), None)[1])
+        h3 = model.roi_heads.predictor.register_forward_hook(
+            lambda m, i, o: feats.__setitem__("pred", [o[0].detach(), o[1].detach()] + [r.detach() for r in o[2]]))
+        from wetectron.modeling.roi_heads.weak_head import pseudo_label_generator as plg
+        captured = []
+        orig = plg.od_layer.__call__
+
+        def spy(self, proposals, source_score, labels_, device, pgt_instance, return_targets=False):
+            r = orig(self, proposals, source_score, labels_, device, pgt_instance, return_targets)
+            captured.append(([p.clone() for p in pgt_instance], [x.clone() for x in r]))
+            return r
+        plg.od_layer.__call__ = spy
+        try:
+            losses, acc = model(il, targets, props)
+        finally:
+            plg.od_layer.__call__ = orig
+        h.remove(); h2.remove(); h3.remove()
     finally:
         db_mod.torch = torch; vgg_mod.torch = torch
     o = {"loss_" + k: v.detach().numpy() for k, v in losses.items()}
+    # discovered pseudo-GT sets / pseudo labels per refinement branch (1 image) and the head outputs they
+    # were mined from: lets the GPU test tell a genuine mismatch from an ulp-level `Sim >= tau` flip
+    for i in range(3):
+        inst, (pl, lw, rt) = captured[i]
+        for c in range(20):
+            if inst[c].numel():
+                o["inst_0_%d_%d" % (i, c)] = inst[c].numpy()
+        o["pl_0_%d" % i] = pl.numpy(); o["lw_0_%d" % i] = lw.numpy()
+    o["simf"] = feats["simf"].numpy()
+    for k, v in zip(("cls", "det", "ref0", "ref1", "ref2"), feats["pred"]):
+        o["head_" + k] = v.numpy()
     o.update({"acc_" + k: np.asarray(float(v)) for k, v in acc.items()})
     f = feats["feat"]
     o["feat_shape"] = np.array(f.shape); o["feat_sample"] = f[0, ::37, ::5, ::7].numpy()

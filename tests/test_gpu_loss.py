@@ -195,10 +195,47 @@ def test_model_cfg1_golden(golden):
         t = BoxList(torch.zeros((len(lab), 4)), (600, 600), "xyxy")
         t.add_field("labels", torch.as_tensor(lab))
         targets.append(t)
+    caught = {}
+    h = model.roi_heads.model_sim.register_forward_hook(
+        lambda m, i, o: (caught.setdefault("simf", o.detach()), None)[1])
     losses, accs = model(images.cuda(), targets, props)
+    h.remove()
+    # Sim_Net embeddings of all proposals vs the reference's (unit rows -> absolute tolerance)
+    assert float((caught["simf"].cpu() - torch.from_numpy(G["simf"])).abs().max()) <= 1e-4
+    # discovered pseudo-GT sets vs the reference's.  `Sim[m] >= tau` (loss.py:324) is decided on the last ulp
+    # of an fp32 dot product and all cosines sit in a 0.1-wide band at random init, so a set
+    # may legitimately differ between MKL and the GPU; a difference is accepted only when the product's own
+    # similarity row has an element within 2e-6 of tau for that (branch, class) -- then the dependent branch
+    # losses are compared loosely.  Otherwise everything is held to 1e-3.
+    st = model.roi_heads.loss_evaluator.last_state
+    inst, cnt = st.inst.cpu().numpy(), st.inst_cnt.cpu().numpy()
+    tau, amax = st.tau.cpu().numpy(), st.amax.cpu().numpy()
+    pair_cls = st.pair_cls.cpu().numpy()
+    Fg = caught["simf"]
+    flipped = []
+    for p in range(st.P):
+        for i in range(3):
+            got = inst[p, i, :cnt[p, i]]
+            exp = G["inst_0_%d_%d" % (i, pair_cls[p])]
+            if not np.array_equal(got, exp):
+                row = (Fg @ Fg[int(amax[p, i])]).cpu().numpy()
+                margin = float(np.abs(row - tau[p, i]).min())
+                # multi-class images: the other class's top proposal m_n is kept or dropped on whether its
+                # self-similarity rounds to > 1.0 (loss.py:327, SURVEY App. A QUIRK) -- also an ulp decision
+                for q in range(st.P):
+                    if q != p:
+                        mn = int(amax[q, i])
+                        margin = min(margin, abs(float(Fg[mn] @ Fg[mn]) - 1.0))
+                flipped.append((i, int(pair_cls[p]), margin, len(got), len(exp)))
+                assert margin <= 2e-6, ("unjustified selection difference", flipped[-1])
+    print("selection flips (branch, class, margin, n_got, n_ref):", flipped)
+    loose = {"loss_ref_cls%d" % i for i, *_ in flipped} | {"loss_ref_reg%d" % i for i, *_ in flipped}
+    if flipped:
+        loose.add("loss_sim")
     for k, v in losses.items():
         ref = float(G["loss_" + k])
-        assert abs(float(v) - ref) <= 1e-3 * abs(ref), (k, float(v), ref)
+        tol = 5e-2 if k in loose else 1e-3
+        assert abs(float(v) - ref) <= tol * abs(ref), (k, float(v), ref, flipped)
     sum(losses.values()).backward()
     gsum = sum(float(p.grad.abs().sum()) for p in model.parameters() if p.grad is not None)
     assert np.isfinite(gsum) and gsum > 0
