@@ -36,6 +36,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--strict-fp32", action="store_true", help="disable TF32 tensor-core math in torch GEMM/conv")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-range", action="store_true",
+                    help="bracket the timed resident steps with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     ap.add_argument("--cpu-sample-props", type=int, default=2000)
     return ap.parse_args()
 
@@ -132,7 +134,7 @@ def make_optimizer(model):
         if "bias" in k:
             lr, wd = 0.01 * 2, 0.0
         params.append({"params": [p], "lr": lr, "weight_decay": wd})
-    return torch.optim.SGD(params, lr=0.01, momentum=0.9, foreach=True)
+    return torch.optim.SGD(params, lr=0.01, momentum=0.9, fused=True)   # one pass over p/g/m per step
 
 
 def run_ours(args):
@@ -221,7 +223,12 @@ def run_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
     l0 = capi.launch_count
+    if args.profile_range:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
     ms = timed(resident_step, args.steps)
+    if args.profile_range:
+        torch.cuda.profiler.stop()
     launches = capi.launch_count - l0
     for _ in range(2):
         e2e_step()

@@ -155,8 +155,16 @@ int odwscl_dropblock_f32(const float* x, const float* centres, int R, int C, int
                          odwscl_stream_t stream);
 
 /* ---- A11 (drop-in for loss.py:319): full N x N similarity F F^T on the tensor cores
- * (tcgen05, 3xTF32 split so the result is fp32-accurate).  out [N,N] fp32. */
-int odwscl_sim_nxn_f32(const float* F, int N, float* out, odwscl_stream_t stream);
+ * (tcgen05.mma kind::tf32 fed by TMA, accumulators in TMEM; 3xTF32 operand split so the result is
+ * fp32-accurate).  out [N,N] fp32; ws sized by odwscl_sim_nxn_ws_bytes(N). */
+size_t odwscl_sim_nxn_ws_bytes(int N);
+int odwscl_sim_nxn_f32(const float* F, int N, float* out, void* ws, size_t ws_bytes, odwscl_stream_t stream);
+
+/* ---- tensor-core building block: C[M,N] = A[M,K] * B[N,K]^T, single-pass TF32 (what torch's
+ * allow_tf32 matmul computes; modeling/backbone/vgg16.py:151,161, sim_net.py:26 run through
+ * cuBLAS in the reference).  K % 4 == 0, ldc >= N, 16-byte aligned A and B. */
+int odwscl_gemm_nt_tf32(const float* A, const float* B, float* C, int M, int N, int K, int ldc,
+                        odwscl_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -24,7 +24,7 @@ _LAUNCHES = {
     "odwscl_roi_align_bwd_f32": 1, "odwscl_box_iou_f32": 1, "odwscl_nms_f32": 1, "odwscl_nms_legacy_f32": 1,
     "odwscl_discover_phase_a_f32": 2, "odwscl_discover_phase_b_f32": 1, "odwscl_bank_assemble": 1,
     "odwscl_supcon_fwd_f32": 2, "odwscl_supcon_bwd_f32": 1, "odwscl_od_layer_f32": 1,
-    "odwscl_dropblock_f32": 3, "odwscl_sim_nxn_f32": 1,
+    "odwscl_dropblock_f32": 3, "odwscl_sim_nxn_f32": 2, "odwscl_gemm_nt_tf32": 1,
 }
 
 _P, _I, _F, _Z = c_void_p, c_int, c_float, c_size_t
@@ -44,7 +44,9 @@ _SIGS = {
     "odwscl_supcon_bwd_f32": (_I, [_P, _P, _I, _P, _P, _P, _P, _I, _F, _P, _P, _P, _P, _P]),
     "odwscl_od_layer_f32": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _I, _P, _P, _F, _P, _P, _P, _P]),
     "odwscl_dropblock_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P]),
-    "odwscl_sim_nxn_f32": (_I, [_P, _I, _P, _P]),
+    "odwscl_sim_nxn_ws_bytes": (_Z, [_I]),
+    "odwscl_sim_nxn_f32": (_I, [_P, _I, _P, _P, _Z, _P]),
+    "odwscl_gemm_nt_tf32": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "odwscl_version": (_I, []),
     "odwscl_strerror": (ctypes.c_char_p, [_I]),
 }
@@ -189,8 +191,21 @@ def sim_nxn(F):
     assert F.shape[1] == 128
     out = torch.empty((F.shape[0], F.shape[0]), dtype=torch.float32, device=F.device)
     with torch.cuda.device(F.device):
-        _call("odwscl_sim_nxn_f32", _ptr(F), F.shape[0], _ptr(out), _stream())
+        ws = _workspace(lib().odwscl_sim_nxn_ws_bytes(F.shape[0]), F.device)
+        _call("odwscl_sim_nxn_f32", _ptr(F), F.shape[0], _ptr(out), _ptr(ws), ws.numel(), _stream())
     return out
+
+
+def gemm_nt_tf32(A, B):
+    """C = A @ B.T with single-pass TF32 tensor-core math (tcgen05)."""
+    A, B = _chk(A, torch.float32, "A"), _chk(B, torch.float32, "B")
+    M, K = A.shape
+    N = B.shape[0]
+    assert B.shape[1] == K and K % 4 == 0
+    C = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    with torch.cuda.device(A.device):
+        _call("odwscl_gemm_nt_tf32", _ptr(A), _ptr(B), _ptr(C), M, N, K, N, _stream())
+    return C
 
 
 def dropblock(x, centres, block, scale_io=None):

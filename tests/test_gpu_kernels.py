@@ -209,8 +209,31 @@ def test_dropblock_vs_oracle(capi, block):
     assert torch.equal(gy, y)
 
 
-def test_sim_nxn(capi):
+@pytest.mark.parametrize("n", [333, 2000])
+def test_sim_nxn(capi, n):
+    """tcgen05 3xTF32 similarity vs the fp32 matmul of loss.py:319 (fp64 as the arbiter)."""
     g = torch.Generator().manual_seed(0)
-    Fm = torch.nn.functional.normalize(torch.randn(333, 128, generator=g), dim=1)
+    Fm = torch.nn.functional.normalize(torch.randn(n, 128, generator=g) + 1.5, dim=1)
     got = capi.sim_nxn(Fm.cuda()).cpu()
-    torch.testing.assert_close(got, Fm @ Fm.T, rtol=1e-5, atol=1e-6)
+    ref64 = (Fm.double() @ Fm.double().T)
+    err = (got.double() - ref64).abs().max().item()
+    err32 = ((Fm @ Fm.T).double() - ref64).abs().max().item()
+    # fp32-class accuracy: the tensor core accumulates with truncation, measured ~4x an MKL sgemm's error
+    assert err <= max(8 * err32, 4e-6), (err, err32)
+    torch.testing.assert_close(got, Fm @ Fm.T, rtol=1e-5, atol=4e-6)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (200, 72, 64), (513, 300, 416), (4000, 4096, 1024)])
+def test_gemm_nt_tf32(capi, M, N, K):
+    """tcgen05 TF32 GEMM.  Inputs carry <= 10 mantissa bits, so TF32 products are exact and the
+    result must match an fp32 matmul to fp32 accumulation error; then generic inputs at TF32 tolerance."""
+    g = torch.Generator().manual_seed(M + N + K)
+    A = (torch.randn(M, K, generator=g) * 8).round() / 8
+    B = (torch.randn(N, K, generator=g) * 8).round() / 8
+    got = capi.gemm_nt_tf32(A.cuda(), B.cuda()).cpu()
+    ref = (A.double() @ B.double().T).float()
+    torch.testing.assert_close(got, ref, rtol=1e-6, atol=1e-5 * K ** 0.5)
+    A, B = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g)
+    got = capi.gemm_nt_tf32(A.cuda(), B.cuda()).cpu()
+    ref = (A.double() @ B.double().T).float()
+    assert float((got - ref).abs().max()) <= 8e-3 * K ** 0.5          # TF32: operands truncated to 10 mantissa bits (2^-10 relative each)
