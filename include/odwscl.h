@@ -166,6 +166,33 @@ int odwscl_sim_nxn_f32(const float* F, int N, float* out, void* ws, size_t ws_by
 int odwscl_gemm_nt_tf32(const float* A, const float* B, float* C, int M, int N, int K, int ldc,
                         odwscl_stream_t stream);
 
+/* ---- A1: the VGG16-OICR conv stack (modeling/backbone/vgg16.py:26-36,58-83; cuDNN via nn.Conv2d in
+ * the reference), channels-last.  3x3 / stride 1 / padding = dilation ("same") convolution as a tcgen05
+ * implicit GEMM fed by TMA (zero-filled out-of-image boxes are the padding):
+ *   y[b,h,w,co] = epilogue( sum_{r,s,ci} x[b, h+(r-1)d, w+(s-1)d, ci] * w_krsc[co,r,s,ci] )
+ * x [B,H,W,Cin], w_krsc [Cout,3,3,Cin], y [B,H,W,Cout]; Cin % 32 == 0, Cout % 32 == 0.  Single-pass TF32
+ * inputs, fp32 accumulation.  flags: 1 = ReLU, 2 = accumulate into y (y += conv; used by the 3-pass
+ * strict-fp32 mode), 4 = zero y where mask_src <= 0 (mask_src [B,H,W,Cout]: fused ReLU derivative, which
+ * makes this entry point the DGRAD as well: x = dY, w_krsc = flipped/transposed weights).  Order of the
+ * epilogue: + bias, + previous y, ReLU, mask.  bias may be NULL. */
+#define ODWSCL_CONV_RELU  1
+#define ODWSCL_CONV_ACCUM 2
+#define ODWSCL_CONV_MASK  4
+int odwscl_conv3x3_nhwc_tf32(const float* x, int B, int H, int W, int Cin, const float* w_krsc,
+                             const float* bias, int Cout, int dilation, int flags, const float* mask_src,
+                             float* y, odwscl_stream_t stream);
+/* conv1_1 (Cin = 3, Cout = 64): fp32 FFMA, reads the NCHW image [B,3,H,W] and torch-layout weights
+ * [64,3,3,3], writes NHWC [B,H,W,64]. */
+int odwscl_conv3x3_c3_f32(const float* x_nchw, int B, int H, int W, const float* w_oihw, const float* bias,
+                          int Cout, int relu, float* y_nhwc, odwscl_stream_t stream);
+/* 2x2 / stride 2 max-pool, NHWC (C % 4 == 0), and its backward (gradient to the first maximum of each
+ * window; relu_mask != 0 additionally zeroes it where the maximum is <= 0). */
+int odwscl_maxpool2x2_nhwc_f32(const float* x, int B, int H, int W, int C, float* y, odwscl_stream_t stream);
+int odwscl_maxpool2x2_nhwc_bwd_f32(const float* x, const float* gy, int B, int H, int W, int C, int relu_mask,
+                                   float* gx, odwscl_stream_t stream);
+/* x = hi + lo with hi = rna_tf32(x), lo = rna_tf32(x - hi): operands of the 3-pass strict-fp32 mode. */
+int odwscl_split_tf32(const float* x, long long n, float* hi, float* lo, odwscl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,6 +25,8 @@ _LAUNCHES = {
     "odwscl_discover_phase_a_f32": 2, "odwscl_discover_phase_b_f32": 1, "odwscl_bank_assemble": 1,
     "odwscl_supcon_fwd_f32": 2, "odwscl_supcon_bwd_f32": 1, "odwscl_od_layer_f32": 1,
     "odwscl_dropblock_f32": 3, "odwscl_sim_nxn_f32": 2, "odwscl_gemm_nt_tf32": 1,
+    "odwscl_conv3x3_nhwc_tf32": 1, "odwscl_conv3x3_c3_f32": 1, "odwscl_maxpool2x2_nhwc_f32": 1,
+    "odwscl_maxpool2x2_nhwc_bwd_f32": 1, "odwscl_split_tf32": 1,
 }
 
 _P, _I, _F, _Z = c_void_p, c_int, c_float, c_size_t
@@ -47,6 +49,11 @@ _SIGS = {
     "odwscl_sim_nxn_ws_bytes": (_Z, [_I]),
     "odwscl_sim_nxn_f32": (_I, [_P, _I, _P, _P, _Z, _P]),
     "odwscl_gemm_nt_tf32": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "odwscl_conv3x3_nhwc_tf32": (_I, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _P, _P, _P]),
+    "odwscl_conv3x3_c3_f32": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _P]),
+    "odwscl_maxpool2x2_nhwc_f32": (_I, [_P, _I, _I, _I, _I, _P, _P]),
+    "odwscl_maxpool2x2_nhwc_bwd_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "odwscl_split_tf32": (_I, [_P, ctypes.c_longlong, _P, _P, _P]),
     "odwscl_version": (_I, []),
     "odwscl_strerror": (ctypes.c_char_p, [_I]),
 }
@@ -220,6 +227,63 @@ def dropblock(x, centres, block, scale_io=None):
         _call("odwscl_dropblock_f32", _ptr(x), _ptr(centres), R, C, ph, pw, int(block), _ptr(y), _ptr(scale_io),
               int(reuse), _stream())
     return y, scale_io
+
+
+# ---------------------------------------------------------------- conv stack (NHWC)
+CONV_RELU, CONV_ACCUM, CONV_MASK = 1, 2, 4
+
+
+def conv3x3_nhwc(x, w_krsc, bias, dilation=1, flags=0, mask_src=None, out=None):
+    """x [B,H,W,Cin], w_krsc [Cout,3,3,Cin] -> y [B,H,W,Cout] (tcgen05 implicit GEMM, TF32)."""
+    x, w_krsc = _chk(x, torch.float32, "x"), _chk(w_krsc, torch.float32, "w")
+    B, H, W, Cin = x.shape
+    Cout = w_krsc.shape[0]
+    assert w_krsc.shape == (Cout, 3, 3, Cin)
+    y = out if out is not None else torch.empty((B, H, W, Cout), dtype=torch.float32, device=x.device)
+    assert y.is_contiguous() and y.shape == (B, H, W, Cout)
+    if mask_src is not None:
+        mask_src = _chk(mask_src, torch.float32, "mask_src")
+        assert mask_src.shape == y.shape
+    with torch.cuda.device(x.device):
+        _call("odwscl_conv3x3_nhwc_tf32", _ptr(x), B, H, W, Cin, _ptr(w_krsc), _ptr(bias), Cout, int(dilation),
+              int(flags), _ptr(mask_src), _ptr(y), _stream())
+    return y
+
+
+def conv3x3_c3(x_nchw, w_oihw, bias, relu=True):
+    x_nchw, w_oihw = _chk(x_nchw, torch.float32, "x"), _chk(w_oihw, torch.float32, "w")
+    B, _, H, W = x_nchw.shape
+    Cout = w_oihw.shape[0]
+    y = torch.empty((B, H, W, Cout), dtype=torch.float32, device=x_nchw.device)
+    with torch.cuda.device(x_nchw.device):
+        _call("odwscl_conv3x3_c3_f32", _ptr(x_nchw), B, H, W, _ptr(w_oihw), _ptr(bias), Cout, int(relu), _ptr(y), _stream())
+    return y
+
+
+def maxpool2x2_nhwc(x):
+    x = _chk(x, torch.float32, "x")
+    B, H, W, C = x.shape
+    y = torch.empty((B, H // 2, W // 2, C), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _call("odwscl_maxpool2x2_nhwc_f32", _ptr(x), B, H, W, C, _ptr(y), _stream())
+    return y
+
+
+def maxpool2x2_nhwc_bwd(x, gy, relu_mask):
+    x, gy = _chk(x, torch.float32, "x"), _chk(gy, torch.float32, "gy")
+    B, H, W, C = x.shape
+    gx = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _call("odwscl_maxpool2x2_nhwc_bwd_f32", _ptr(x), _ptr(gy), B, H, W, C, int(relu_mask), _ptr(gx), _stream())
+    return gx
+
+
+def split_tf32(x):
+    x = _chk(x, torch.float32, "x")
+    hi, lo = torch.empty_like(x), torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _call("odwscl_split_tf32", _ptr(x), x.numel(), _ptr(hi), _ptr(lo), _stream())
+    return hi, lo
 
 
 # ---------------------------------------------------------------- object discovery / SupCon

@@ -1,0 +1,342 @@
+// conv3x3.cu -- the VGG16-OICR conv stack (modeling/backbone/vgg16.py:26-36,58-83)
+// as hand-written sm_100a kernels, channels-last (NHWC) end to end.
+//
+//   conv3x3_tf32_kernel   3x3 / stride 1 / "same" padding / dilation 1 or 2 convolution as an IMPLICIT
+//                         GEMM on the tensor cores:  Y[pixel, co] = sum_{tap, ci} X[pixel + tap, ci] W[co, tap, ci]
+//                         M = 128 output pixels (a TH x TW patch of one image), N = BN output channels,
+//                         K = 9 taps x Cin.  For every (tap, 32-channel slab) the producer issues ONE 4-D
+//                         TMA box load of the NHWC input shifted by the tap offset -- out-of-image rows /
+//                         columns are zero-filled by the TMA unit, which IS the conv padding -- plus one
+//                         2-D box of the K-major weight matrix; tcgen05.mma.kind::tf32 accumulates in TMEM;
+//                         the epilogue fuses bias, ReLU, accumulate-into-output (3xTF32 strict mode) and a
+//                         ReLU-derivative mask (so the same kernel is the DGRAD: dX = conv(dY, W flipped/transposed),
+//                         masked by the previous activation).
+//   conv3x3_c3_kernel     conv1_1 (Cin = 3, K = 27: not tensor-core shaped, output-bandwidth bound): fp32 FFMA,
+//                         reads the NCHW image, writes NHWC.
+//   maxpool2x2_*          2x2 / stride 2 max-pool forward and backward (first-max routing as torch).
+//   split_tf32            x -> (hi, lo) for the 3-pass strict-fp32 mode used by the parity tests.
+//
+// Reference arithmetic: cuDNN through torch.nn.Conv2d; TF32 is what torch 1.7.1 (the reference's pin,
+// README.md:23) runs by default on tensor-core GPUs.  Single-pass mode = TF32 inputs / fp32 accumulate.
+#include "common.cuh"
+#include "tc_sm100.cuh"
+
+namespace {
+
+constexpr int kBM = 128;
+enum : int { kRelu = 1, kAccum = 2, kMask = 4 };
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, (STAGES * (kBM + BN) * 128 + 2048 <= 110 * 1024) ? 2 : 1)
+conv3x3_tf32_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                    const float* __restrict__ bias, const float* __restrict__ mask_src, float* __restrict__ y,
+                    int H, int W, int Cin, int Cout, int tw_log2, int tiles_w, int tiles_h, int dil, int flags) {
+  constexpr int A_BYTES = kBM * tc::kTileKBytes, B_BYTES = BN * tc::kTileKBytes, STAGE_BYTES = A_BYTES + B_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar;
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int TW = 1 << tw_log2, TH = kBM >> tw_log2;
+  int t = blockIdx.x;
+  const int tx = t % tiles_w; t /= tiles_w;
+  const int ty = t % tiles_h;
+  const int b = t / tiles_h;
+  const int w0 = tx * TW, h0 = ty * TH;
+  const int n0 = blockIdx.y * BN;
+  const int cchunks = Cin / tc::kTileK;
+  const int kiters = 9 * cchunks;
+
+  if (warp == 0 && tc::elect_one()) {
+    tc::tma_prefetch_desc(&map_x);
+    tc::tma_prefetch_desc(&map_w);
+    for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+    tc::mbar_init(&tmem_full_bar, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(&tmem_base_s, BN);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    if (tc::elect_one()) {
+      int tap = 0, cc = 0;
+      for (int it = 0; it < kiters; ++it) {
+        const int s = it % STAGES;
+        tc::mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+        tc::mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+        uint8_t* a = tiles + (size_t)s * STAGE_BYTES;
+        const int r = tap / 3, q = tap - 3 * r;
+        // input patch shifted by the tap; rows / columns outside the image arrive as zeros (= padding)
+        tc::tma_load_4d(a, &map_x, &full_bar[s], cc * tc::kTileK, w0 + (q - 1) * dil, h0 + (r - 1) * dil, b);
+        tc::tma_load_2d(a + A_BYTES, &map_w, &full_bar[s], tap * Cin + cc * tc::kTileK, n0);
+        if (++cc == cchunks) { cc = 0; ++tap; }
+      }
+    }
+  } else if (warp == 1) {
+    if (tc::elect_one()) {
+      constexpr uint32_t idesc = tc::umma_idesc_tf32(kBM, BN);
+      for (int it = 0; it < kiters; ++it) {
+        const int s = it % STAGES;
+        tc::mbar_wait(&full_bar[s], (it / STAGES) & 1);
+        tc::tc_fence_after();
+        const uint32_t a = tc::smem_u32(tiles + (size_t)s * STAGE_BYTES);
+        const uint64_t ad = tc::umma_desc_sw128(a), bd = tc::umma_desc_sw128(a + A_BYTES);
+#pragma unroll
+        for (int k = 0; k < tc::kTileK / tc::kUmmaK; ++k)
+          tc::umma_tf32(tmem_base, ad + 2 * k, bd + 2 * k, idesc, (it | k) != 0);
+        tc::umma_commit(&empty_bar[s]);
+      }
+      tc::umma_commit(&tmem_full_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int h = h0 + (row >> tw_log2), w = w0 + (row & (TW - 1));
+    const bool valid = (h < H) && (w < W);
+    const size_t pix = ((size_t)b * H + h) * W + w;
+    tc::mbar_wait(&tmem_full_bar, 0);
+    tc::tc_fence_after();
+    float v[32];
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, v);
+      tc::tmem_ld_wait();
+      const int co = n0 + c * 32;
+      if (!valid || co >= Cout) continue;
+      float4* dst = reinterpret_cast<float4*>(y + pix * Cout + co);
+      const float4* msk = reinterpret_cast<const float4*>(mask_src + pix * Cout + co);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        if (bias != nullptr) {
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + co) + j);
+          o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+        }
+        if (flags & kAccum) {
+          const float4 p = dst[j];
+          o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+        }
+        if (flags & kRelu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        if (flags & kMask) {
+          const float4 m = __ldg(msk + j);
+          o.x = m.x > 0.f ? o.x : 0.f; o.y = m.y > 0.f ? o.y : 0.f; o.z = m.z > 0.f ? o.z : 0.f; o.w = m.w > 0.f ? o.w : 0.f;
+        }
+        dst[j] = o;
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, BN);
+}
+
+template <int BN, int STAGES>
+int launch_conv(const float* x, int B, int H, int W, int Cin, const float* wk, const float* bias, int Cout, int dil,
+                int flags, const float* mask_src, float* y, cudaStream_t st) {
+  // output patch shape: TH x TW = 128 pixels, minimising the padded area (ties -> wider rows)
+  int best_log2 = 3;
+  long long best_area = -1;
+  for (int l = 3; l <= 7; ++l) {
+    const int TW = 1 << l, TH = kBM >> l;
+    const long long area = (long long)odw_cdiv(H, TH) * TH * odw_cdiv(W, TW) * TW;
+    if (best_area < 0 || area <= best_area) { best_area = area; best_log2 = l; }
+  }
+  const int TW = 1 << best_log2, TH = kBM >> best_log2;
+  const int tiles_w = odw_cdiv(W, TW), tiles_h = odw_cdiv(H, TH);
+  CUtensorMap mx, mw;
+  const uint64_t dx[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+  const uint64_t sx[3] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4};
+  const uint32_t bx[4] = {32, (uint32_t)TW, (uint32_t)TH, 1};
+  int rc = tc::make_tmap_f32(&mx, x, 4, dx, sx, bx);
+  if (rc) return rc;
+  const uint64_t dw[2] = {(uint64_t)9 * Cin, (uint64_t)Cout};
+  const uint64_t sw[1] = {(uint64_t)9 * Cin * 4};
+  const uint32_t bw[2] = {32, (uint32_t)BN};
+  rc = tc::make_tmap_f32(&mw, wk, 2, dw, sw, bw);
+  if (rc) return rc;
+  const int smem = STAGES * (kBM + BN) * tc::kTileKBytes + 1024;
+  ODW_CUDA(cudaFuncSetAttribute(conv3x3_tf32_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  dim3 grid(B * tiles_h * tiles_w, odw_cdiv(Cout, BN));
+  conv3x3_tf32_kernel<BN, STAGES><<<grid, 192, smem, st>>>(mx, mw, bias, mask_src ? mask_src : y, y, H, W, Cin, Cout,
+                                                            best_log2, tiles_w, tiles_h, dil, flags);
+  ODW_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// conv1_1: Cin = 3.  thread = (pixel, 16-channel group); 4 adjacent lanes write one pixel's 64 channels.
+template <int COUT>
+__global__ void __launch_bounds__(256)
+conv3x3_c3_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                  float* __restrict__ y, int B, int H, int W, int relu) {
+  constexpr int G = COUT / 16;
+  __shared__ float sw[27 * COUT];     // [tap*3+ci][co]
+  __shared__ float sb[COUT];
+  for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) {
+    const int co = i % COUT, k = i / COUT;          // k = (r*3+s)*3 + ci ; torch layout [co][ci][r][s]
+    const int ci = k % 3, tap = k / 3;
+    sw[i] = w[(co * 3 + ci) * 9 + tap];
+  }
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) sb[i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  const long long total = (long long)B * H * W * G;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % G);
+    const long long pix = idx / G;
+    const int wq = (int)(pix % W);
+    const int hq = (int)((pix / W) % H);
+    const int bq = (int)(pix / ((long long)W * H));
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = sb[g * 16 + j];
+    const float* xb = x + (size_t)bq * 3 * H * W;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int hh = hq + r - 1;
+      if (hh < 0 || hh >= H) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int ww = wq + s - 1;
+        if (ww < 0 || ww >= W) continue;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) {
+          const float xv = __ldg(xb + ((size_t)ci * H + hh) * W + ww);
+          const float* wr = sw + ((r * 3 + s) * 3 + ci) * COUT + g * 16;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] = fmaf(xv, wr[j], acc[j]);
+        }
+      }
+    }
+    float4* dst = reinterpret_cast<float4*>(y + (size_t)pix * COUT + g * 16);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float4 o = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+      if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+      dst[j] = o;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void maxpool2x2_nhwc_kernel(const float4* __restrict__ x, float4* __restrict__ y, int B, int H, int W, int C4) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)B * Ho * Wo * C4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4);
+    long long p = i / C4;
+    const int wo = (int)(p % Wo); p /= Wo;
+    const int ho = (int)(p % Ho);
+    const int b = (int)(p / Ho);
+    const float4* s = x + (((size_t)b * H + 2 * ho) * W + 2 * wo) * C4 + c;
+    const float4 a = __ldg(s), bb = __ldg(s + C4), cc = __ldg(s + (size_t)W * C4), d = __ldg(s + (size_t)W * C4 + C4);
+    float4 o;
+    o.x = fmaxf(fmaxf(a.x, bb.x), fmaxf(cc.x, d.x)); o.y = fmaxf(fmaxf(a.y, bb.y), fmaxf(cc.y, d.y));
+    o.z = fmaxf(fmaxf(a.z, bb.z), fmaxf(cc.z, d.z)); o.w = fmaxf(fmaxf(a.w, bb.w), fmaxf(cc.w, d.w));
+    y[i] = o;
+  }
+}
+
+// gx = grad routed to the FIRST maximal element of each 2x2 window (torch max_pool2d semantics), optionally
+// multiplied by the ReLU derivative of x (x is a post-ReLU activation: derivative 0 where x == 0).
+__global__ void maxpool2x2_nhwc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ gx,
+                                           int B, int H, int W, int C, int relu_mask) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)B * H * W * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long p = i / C;
+    const int w = (int)(p % W); p /= W;
+    const int h = (int)(p % H);
+    const int b = (int)(p / H);
+    const int ho = h >> 1, wo = w >> 1;
+    float g = 0.f;
+    if (ho < Ho && wo < Wo) {
+      const float* s = x + (((size_t)b * H + 2 * ho) * W + 2 * wo) * C + c;
+      const float v0 = s[0], v1 = s[C], v2 = s[(size_t)W * C], v3 = s[(size_t)W * C + C];
+      int am = 0; float m = v0;
+      if (v1 > m) { m = v1; am = 1; }
+      if (v2 > m) { m = v2; am = 2; }
+      if (v3 > m) { m = v3; am = 3; }
+      const int me = ((h & 1) << 1) | (w & 1);
+      if (me == am && !(relu_mask && !(m > 0.f))) g = gy[(((size_t)b * Ho + ho) * Wo + wo) * C + c];
+    }
+    gx[i] = g;
+  }
+}
+
+__global__ void split_tf32_kernel(const float* __restrict__ x, long long n, float* __restrict__ hi, float* __restrict__ lo) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    uint32_t hb, lb;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+    const float h = __uint_as_float(hb);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(__fsub_rn(v, h)));
+    hi[i] = h;
+    lo[i] = __uint_as_float(lb);
+  }
+}
+
+}  // namespace
+
+ODW_API int odwscl_conv3x3_nhwc_tf32(const float* x, int B, int H, int W, int Cin, const float* w_krsc,
+                                     const float* bias, int Cout, int dilation, int flags, const float* mask_src,
+                                     float* y, odwscl_stream_t stream) {
+  if (B < 0 || H < 0 || W < 0 || Cin <= 0 || Cout <= 0 || (Cin % 32) || (Cout % 32) || dilation < 1) return ODWSCL_EINVAL;
+  if ((long long)B * H * W == 0) return 0;
+  if (!x || !w_krsc || !y || ((flags & kMask) && !mask_src)) return ODWSCL_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (Cout % 256 == 0) return launch_conv<256, 4>(x, B, H, W, Cin, w_krsc, bias, Cout, dilation, flags, mask_src, y, st);
+  if (Cout % 128 == 0) return launch_conv<128, 3>(x, B, H, W, Cin, w_krsc, bias, Cout, dilation, flags, mask_src, y, st);
+  if (Cout % 64 == 0) return launch_conv<64, 4>(x, B, H, W, Cin, w_krsc, bias, Cout, dilation, flags, mask_src, y, st);
+  return launch_conv<32, 4>(x, B, H, W, Cin, w_krsc, bias, Cout, dilation, flags, mask_src, y, st);
+}
+
+ODW_API int odwscl_conv3x3_c3_f32(const float* x_nchw, int B, int H, int W, const float* w_oihw, const float* bias,
+                                  int Cout, int relu, float* y_nhwc, odwscl_stream_t stream) {
+  if (B < 0 || H < 0 || W < 0 || Cout != 64) return ODWSCL_EINVAL;
+  if ((long long)B * H * W == 0) return 0;
+  if (!x_nchw || !w_oihw || !y_nhwc) return ODWSCL_EINVAL;
+  const long long total = (long long)B * H * W * 4;
+  const int blocks = (int)min((long long)ODW_NUM_SMS * 8, (total + 255) / 256);
+  conv3x3_c3_kernel<64><<<blocks, 256, 0, (cudaStream_t)stream>>>(x_nchw, w_oihw, bias, y_nhwc, B, H, W, relu);
+  ODW_LAUNCH_CHECK();
+  return 0;
+}
+
+ODW_API int odwscl_maxpool2x2_nhwc_f32(const float* x, int B, int H, int W, int C, float* y, odwscl_stream_t stream) {
+  if (B < 0 || H < 0 || W < 0 || C <= 0 || (C & 3)) return ODWSCL_EINVAL;
+  const long long total = (long long)B * (H / 2) * (W / 2) * (C / 4);
+  if (total == 0) return 0;
+  if (!x || !y) return ODWSCL_EINVAL;
+  const int blocks = (int)min((long long)ODW_NUM_SMS * 16, (total + 255) / 256);
+  maxpool2x2_nhwc_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(x),
+                                                                   reinterpret_cast<float4*>(y), B, H, W, C / 4);
+  ODW_LAUNCH_CHECK();
+  return 0;
+}
+
+ODW_API int odwscl_maxpool2x2_nhwc_bwd_f32(const float* x, const float* gy, int B, int H, int W, int C, int relu_mask,
+                                           float* gx, odwscl_stream_t stream) {
+  if (B < 0 || H < 0 || W < 0 || C <= 0) return ODWSCL_EINVAL;
+  const long long total = (long long)B * H * W * C;
+  if (total == 0) return 0;
+  if (!x || !gy || !gx) return ODWSCL_EINVAL;
+  const int blocks = (int)min((long long)ODW_NUM_SMS * 16, (total + 255) / 256);
+  maxpool2x2_nhwc_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, gy, gx, B, H, W, C, relu_mask);
+  ODW_LAUNCH_CHECK();
+  return 0;
+}
+
+ODW_API int odwscl_split_tf32(const float* x, long long n, float* hi, float* lo, odwscl_stream_t stream) {
+  if (n < 0) return ODWSCL_EINVAL;
+  if (n == 0) return 0;
+  if (!x || !hi || !lo) return ODWSCL_EINVAL;
+  const int blocks = (int)min((long long)ODW_NUM_SMS * 16, (n + 255) / 256);
+  split_tf32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, n, hi, lo);
+  ODW_LAUNCH_CHECK();
+  return 0;
+}

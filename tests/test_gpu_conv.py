@@ -1,0 +1,113 @@
+"""GPU parity of the hand-written conv stack kernels (csrc/conv3x3.cu) against torch's fp32 convolution /
+max-pool (the reference computes these through nn.Conv2d / nn.MaxPool2d, modeling/backbone/vgg16.py:58-83).
+TF32 tolerance is stated per test; inputs with <= 10 mantissa bits make TF32 products exact."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from odwscl_b200 import capi as c
+    c.lib()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return c
+
+
+def q(t, s=8):
+    return (t * s).round() / s
+
+
+def ref_conv(x_nhwc, w_oihw, bias, dil):
+    y = F.conv2d(x_nhwc.permute(0, 3, 1, 2).double(), w_oihw.double(), None if bias is None else bias.double(),
+                 padding=dil, dilation=dil)
+    return y.permute(0, 2, 3, 1).float().contiguous()
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,dil", [
+    (1, 8, 16, 32, 32, 1), (2, 19, 27, 64, 64, 1), (1, 38, 50, 64, 128, 1), (1, 20, 128, 128, 256, 1),
+    (2, 13, 21, 256, 512, 2), (1, 76, 128, 512, 512, 2), (1, 9, 300, 32, 96, 1)])
+def test_conv3x3_exact_inputs(capi, B, H, W, Cin, Cout, dil):
+    g = torch.Generator().manual_seed(B * 1000 + H + W + Cin + Cout)
+    x = q(torch.randn(B, H, W, Cin, generator=g)).cuda()
+    w = q(torch.randn(Cout, Cin, 3, 3, generator=g) * 0.5, 16).cuda()
+    b = q(torch.randn(Cout, generator=g)).cuda()
+    wk = w.permute(0, 2, 3, 1).contiguous()
+    ref = ref_conv(x, w, b, dil)
+    got = capi.conv3x3_nhwc(x, wk, b, dilation=dil)
+    torch.testing.assert_close(got, ref, rtol=2e-6, atol=2e-5 * (9 * Cin) ** 0.5)
+    got = capi.conv3x3_nhwc(x, wk, b, dilation=dil, flags=capi.CONV_RELU)
+    torch.testing.assert_close(got, ref.clamp_min(0), rtol=2e-6, atol=2e-5 * (9 * Cin) ** 0.5)
+    # accumulate + mask: y = mask(relu(prev + conv))
+    prev = q(torch.randn(B, H, W, Cout, generator=g)).cuda()
+    msk = torch.randn(B, H, W, Cout, generator=g).cuda()
+    got = capi.conv3x3_nhwc(x, wk, None, dilation=dil, flags=capi.CONV_ACCUM | capi.CONV_RELU | capi.CONV_MASK,
+                            mask_src=msk, out=prev.clone())
+    exp = (prev + ref_conv(x, w, None, dil)).clamp_min(0) * (msk > 0)
+    torch.testing.assert_close(got, exp, rtol=2e-6, atol=2e-5 * (9 * Cin) ** 0.5)
+
+
+@pytest.mark.parametrize("Cin,Cout,dil", [(64, 128, 1), (512, 512, 2)])
+def test_conv3x3_tf32_and_strict(capi, Cin, Cout, dil):
+    """generic fp32 inputs: single pass within TF32 tolerance; 3-pass hi/lo split within 2e-5 of fp32."""
+    g = torch.Generator().manual_seed(Cin + dil)
+    B, H, W = 2, 30, 44
+    x = torch.randn(B, H, W, Cin, generator=g).cuda()
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) * (2.0 / (9 * Cin)) ** 0.5).cuda()
+    b = torch.randn(Cout, generator=g).cuda()
+    wk = w.permute(0, 2, 3, 1).contiguous()
+    ref = ref_conv(x, w, b, dil)
+    scale = float(ref.abs().max())
+    got = capi.conv3x3_nhwc(x, wk, b, dilation=dil)
+    assert float((got - ref).abs().max()) <= 3e-3 * scale               # TF32: 2^-10 relative per operand
+    xh, xl = capi.split_tf32(x)
+    wh, wl = capi.split_tf32(wk)
+    y = capi.conv3x3_nhwc(xh, wh, b, dilation=dil)
+    capi.conv3x3_nhwc(xh, wl, None, dilation=dil, flags=capi.CONV_ACCUM, out=y)
+    capi.conv3x3_nhwc(xl, wh, None, dilation=dil, flags=capi.CONV_ACCUM, out=y)
+    assert float((y - ref).abs().max()) <= 2e-5 * scale
+
+
+def test_conv_dgrad_via_forward_kernel(capi):
+    """dX = conv(dY, W flipped & transposed) masked by the ReLU derivative == autograd of relu(conv)."""
+    g = torch.Generator().manual_seed(5)
+    B, H, W, Cin, Cout, dil = 1, 21, 37, 64, 96, 2
+    a_prev = q(torch.randn(B, H, W, Cin, generator=g)).clamp_min(0).cuda()       # post-ReLU activation feeding the layer
+    w = q(torch.randn(Cout, Cin, 3, 3, generator=g) * 0.5, 16).cuda()
+    dy = q(torch.randn(B, H, W, Cout, generator=g)).cuda()
+    xin = a_prev.permute(0, 3, 1, 2).double().requires_grad_(True)
+    yy = F.conv2d(xin, w.double(), None, padding=dil, dilation=dil)
+    (gx,) = torch.autograd.grad(yy, xin, dy.permute(0, 3, 1, 2).double())
+    exp = (gx.permute(0, 2, 3, 1).float() * (a_prev > 0)).contiguous()
+    wd = w.flip(2, 3).permute(1, 2, 3, 0).contiguous()                           # [Cin, 3, 3, Cout]
+    got = capi.conv3x3_nhwc(dy, wd, None, dilation=dil, flags=capi.CONV_MASK, mask_src=a_prev)
+    torch.testing.assert_close(got, exp, rtol=2e-6, atol=1e-3)
+
+
+def test_conv1_1_c3(capi):
+    g = torch.Generator().manual_seed(6)
+    x = (torch.randn(2, 3, 45, 70, generator=g) * 50).cuda()
+    w = (torch.randn(64, 3, 3, 3, generator=g) * 0.2).cuda()
+    b = torch.randn(64, generator=g).cuda()
+    ref = F.relu(F.conv2d(x.double(), w.double(), b.double(), padding=1)).permute(0, 2, 3, 1).float()
+    got = capi.conv3x3_c3(x, w, b, relu=True)
+    torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-3)
+
+
+def test_maxpool_nhwc(capi):
+    g = torch.Generator().manual_seed(7)
+    x = q(torch.randn(2, 19, 30, 64, generator=g), 2).clamp_min(0).cuda()        # plateaus / ties / zeros
+    xn = x.permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    yn = F.max_pool2d(xn, 2, 2)
+    got = capi.maxpool2x2_nhwc(x)
+    assert torch.equal(got, yn.permute(0, 2, 3, 1).contiguous())
+    gy = torch.randn(yn.shape, generator=g).cuda()
+    (gx,) = torch.autograd.grad(yn, xn, gy)
+    gyn = gy.permute(0, 2, 3, 1).contiguous()
+    got = capi.maxpool2x2_nhwc_bwd(x, gyn, relu_mask=False)
+    assert torch.equal(got, gx.permute(0, 2, 3, 1).contiguous())
+    got = capi.maxpool2x2_nhwc_bwd(x, gyn, relu_mask=True)
+    assert torch.equal(got, (gx.permute(0, 2, 3, 1) * (x > 0)).contiguous())
