@@ -53,6 +53,13 @@ int odwscl_roi_pool_bwd_f32(const float* grad_out, const int32_t* argmax, const 
                             int B, int C, int H, int W, int ph, int pw, float* grad_in,
                             odwscl_stream_t stream);
 
+/* Channels-last variants of A3 / A4 for the model path (the conv stack below is NHWC): feat_nhwc and
+ * grad_in_nhwc are [B,H,W,C]; out / argmax / grad_out keep [R,C,7,7].  7x7 bins, C % 4 == 0. */
+int odwscl_roi_pool_fwd_nhwc_f32(const float* feat_nhwc, int B, int C, int H, int W, const float* rois, int R,
+                                 float scale, float* out, int32_t* argmax, odwscl_stream_t stream);
+int odwscl_roi_pool_bwd_nhwc_f32(const float* grad_out, const int32_t* argmax, const float* rois, int R, int B,
+                                 int C, int H, int W, float* grad_in_nhwc, odwscl_stream_t stream);
+
 /* ---- A5: ROIAlign (legacy, non-aligned).  Replaces _C.roi_align_forward/backward
  * (csrc/ROIAlign.h:11-45 -> csrc/cuda/ROIAlign_cuda.cu:64-122,177-254). */
 int odwscl_roi_align_fwd_f32(const float* feat, int B, int C, int H, int W, const float* rois, int R,
@@ -174,15 +181,19 @@ int odwscl_gemm_nt_tf32(const float* A, const float* B, float* C, int M, int N, 
  * inputs, fp32 accumulation.  flags: 1 = ReLU, 2 = accumulate into y (y += conv; used by the 3-pass
  * strict-fp32 mode), 4 = zero y where mask_src <= 0 (mask_src [B,H,W,Cout]: fused ReLU derivative, which
  * makes this entry point the DGRAD as well: x = dY, w_krsc = flipped/transposed weights).  Order of the
- * epilogue: + bias, + previous y, ReLU, mask.  bias may be NULL. */
+ * epilogue: + bias, + previous y, ReLU, mask, round.  bias may be NULL.  8 = round the result to TF32
+ * (round-to-nearest): the tensor core TRUNCATES fp32 operands to 10 mantissa bits, which biases every
+ * product low; activations that feed another convolution are therefore stored pre-rounded (cuDNN's TF32
+ * kernels round on load -- same arithmetic, no per-layer shrink). */
 #define ODWSCL_CONV_RELU  1
 #define ODWSCL_CONV_ACCUM 2
 #define ODWSCL_CONV_MASK  4
+#define ODWSCL_CONV_ROUND 8
 int odwscl_conv3x3_nhwc_tf32(const float* x, int B, int H, int W, int Cin, const float* w_krsc,
                              const float* bias, int Cout, int dilation, int flags, const float* mask_src,
                              float* y, odwscl_stream_t stream);
 /* conv1_1 (Cin = 3, Cout = 64): fp32 FFMA, reads the NCHW image [B,3,H,W] and torch-layout weights
- * [64,3,3,3], writes NHWC [B,H,W,64]. */
+ * [64,3,3,3], writes NHWC [B,H,W,64].  `relu` is a flag mask: ODWSCL_CONV_RELU | ODWSCL_CONV_ROUND. */
 int odwscl_conv3x3_c3_f32(const float* x_nchw, int B, int H, int W, const float* w_oihw, const float* bias,
                           int Cout, int relu, float* y_nhwc, odwscl_stream_t stream);
 /* 2x2 / stride 2 max-pool, NHWC (C % 4 == 0), and its backward (gradient to the first maximum of each
@@ -190,7 +201,8 @@ int odwscl_conv3x3_c3_f32(const float* x_nchw, int B, int H, int W, const float*
 int odwscl_maxpool2x2_nhwc_f32(const float* x, int B, int H, int W, int C, float* y, odwscl_stream_t stream);
 int odwscl_maxpool2x2_nhwc_bwd_f32(const float* x, const float* gy, int B, int H, int W, int C, int relu_mask,
                                    float* gx, odwscl_stream_t stream);
-/* x = hi + lo with hi = rna_tf32(x), lo = rna_tf32(x - hi): operands of the 3-pass strict-fp32 mode. */
+/* x = hi + lo with hi = rna_tf32(x), lo = rna_tf32(x - hi): operands of the 3-pass strict-fp32 mode.
+ * lo may be NULL (plain rounding of weights / incoming gradients to TF32; hi may alias x). */
 int odwscl_split_tf32(const float* x, long long n, float* hi, float* lo, odwscl_stream_t stream);
 
 #ifdef __cplusplus

@@ -20,7 +20,8 @@ launch_count = 0          # kernels-launching C-ABI calls made so far (bench.py 
 
 # kernels enqueued per entry point (for the `gpu_launches` bench key)
 _LAUNCHES = {
-    "odwscl_roi_pool_fwd_f32": 2, "odwscl_roi_pool_bwd_f32": 1, "odwscl_roi_align_fwd_f32": 1,
+    "odwscl_roi_pool_fwd_f32": 2, "odwscl_roi_pool_bwd_f32": 1, "odwscl_roi_pool_fwd_nhwc_f32": 1,
+    "odwscl_roi_pool_bwd_nhwc_f32": 1, "odwscl_roi_align_fwd_f32": 1,
     "odwscl_roi_align_bwd_f32": 1, "odwscl_box_iou_f32": 1, "odwscl_nms_f32": 1, "odwscl_nms_legacy_f32": 1,
     "odwscl_discover_phase_a_f32": 2, "odwscl_discover_phase_b_f32": 1, "odwscl_bank_assemble": 1,
     "odwscl_supcon_fwd_f32": 2, "odwscl_supcon_bwd_f32": 1, "odwscl_od_layer_f32": 1,
@@ -34,6 +35,8 @@ _SIGS = {
     "odwscl_roi_pool_fwd_ws_bytes": (_Z, [_I] * 7),
     "odwscl_roi_pool_fwd_f32": (_I, [_P, _I, _I, _I, _I, _P, _I, _F, _I, _I, _P, _P, _P, _Z, _P]),
     "odwscl_roi_pool_bwd_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "odwscl_roi_pool_fwd_nhwc_f32": (_I, [_P, _I, _I, _I, _I, _P, _I, _F, _P, _P, _P]),
+    "odwscl_roi_pool_bwd_nhwc_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "odwscl_roi_align_fwd_f32": (_I, [_P, _I, _I, _I, _I, _P, _I, _F, _I, _I, _I, _P, _P]),
     "odwscl_roi_align_bwd_f32": (_I, [_P, _P, _I, _F, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "odwscl_box_iou_f32": (_I, [_P, _I, _P, _I, _I, _P, _P]),
@@ -115,27 +118,44 @@ def _workspace(nbytes, device):
 
 
 # ------------------------------------------------------------------------------------------
+def _is_nhwc(t):
+    """NCHW-shaped tensor whose memory is channels-last (what the conv stack hands to the pooler)."""
+    return t.dim() == 4 and t.shape[1] > 1 and not t.is_contiguous() and t.is_contiguous(memory_format=torch.channels_last)
+
+
 def roi_pool_forward(feat, rois, scale, ph, pw):
-    feat, rois = _chk(feat, torch.float32, "input"), _chk(rois, torch.float32, "rois")
+    rois = _chk(rois, torch.float32, "rois")
     B, C, H, W = feat.shape
     R = rois.shape[0]
+    nhwc = _is_nhwc(feat) and ph == 7 and pw == 7 and C % 4 == 0 and feat.dtype == torch.float32 and feat.is_cuda
+    if not nhwc:
+        feat = _chk(feat, torch.float32, "input")
     out = torch.empty((R, C, ph, pw), dtype=torch.float32, device=feat.device)
     arg = torch.empty((R, C, ph, pw), dtype=torch.int32, device=feat.device)
     if out.numel() == 0:
         return out, arg
     with torch.cuda.device(feat.device):
-        n = lib().odwscl_roi_pool_fwd_ws_bytes(B, C, H, W, R, ph, pw)
-        ws = _workspace(n, feat.device)
-        _call("odwscl_roi_pool_fwd_f32", _ptr(feat), B, C, H, W, _ptr(rois), R, float(scale), ph, pw,
-              _ptr(out), _ptr(arg), _ptr(ws), ws.numel(), _stream())
+        if nhwc:            # memory is already [B,H,W,C]: no transpose pass
+            _call("odwscl_roi_pool_fwd_nhwc_f32", _ptr(feat), B, C, H, W, _ptr(rois), R, float(scale), _ptr(out),
+                  _ptr(arg), _stream())
+        else:
+            n = lib().odwscl_roi_pool_fwd_ws_bytes(B, C, H, W, R, ph, pw)
+            ws = _workspace(n, feat.device)
+            _call("odwscl_roi_pool_fwd_f32", _ptr(feat), B, C, H, W, _ptr(rois), R, float(scale), ph, pw,
+                  _ptr(out), _ptr(arg), _ptr(ws), ws.numel(), _stream())
     return out, arg
 
 
-def roi_pool_backward(grad, rois, argmax, ph, pw, B, C, H, W):
+def roi_pool_backward(grad, rois, argmax, ph, pw, B, C, H, W, channels_last=False):
     grad, rois = _chk(grad, torch.float32, "grad"), _chk(rois, torch.float32, "rois")
     argmax = _chk(argmax, torch.int32, "argmax")
-    gin = torch.empty((B, C, H, W), dtype=torch.float32, device=grad.device)
     with torch.cuda.device(grad.device):
+        if channels_last and ph == 7 and pw == 7:
+            gin = torch.empty((B, H, W, C), dtype=torch.float32, device=grad.device)
+            _call("odwscl_roi_pool_bwd_nhwc_f32", _ptr(grad), _ptr(argmax), _ptr(rois), rois.shape[0], B, C, H, W,
+                  _ptr(gin), _stream())
+            return gin.permute(0, 3, 1, 2)
+        gin = torch.empty((B, C, H, W), dtype=torch.float32, device=grad.device)
         _call("odwscl_roi_pool_bwd_f32", _ptr(grad), _ptr(argmax), _ptr(rois), rois.shape[0], B, C, H, W, ph, pw,
               _ptr(gin), _stream())
     return gin
@@ -230,7 +250,7 @@ def dropblock(x, centres, block, scale_io=None):
 
 
 # ---------------------------------------------------------------- conv stack (NHWC)
-CONV_RELU, CONV_ACCUM, CONV_MASK = 1, 2, 4
+CONV_RELU, CONV_ACCUM, CONV_MASK, CONV_ROUND = 1, 2, 4, 8
 
 
 def conv3x3_nhwc(x, w_krsc, bias, dilation=1, flags=0, mask_src=None, out=None):
@@ -250,13 +270,14 @@ def conv3x3_nhwc(x, w_krsc, bias, dilation=1, flags=0, mask_src=None, out=None):
     return y
 
 
-def conv3x3_c3(x_nchw, w_oihw, bias, relu=True):
+def conv3x3_c3(x_nchw, w_oihw, bias, relu=True, round_tf32=False):
     x_nchw, w_oihw = _chk(x_nchw, torch.float32, "x"), _chk(w_oihw, torch.float32, "w")
     B, _, H, W = x_nchw.shape
     Cout = w_oihw.shape[0]
     y = torch.empty((B, H, W, Cout), dtype=torch.float32, device=x_nchw.device)
     with torch.cuda.device(x_nchw.device):
-        _call("odwscl_conv3x3_c3_f32", _ptr(x_nchw), B, H, W, _ptr(w_oihw), _ptr(bias), Cout, int(relu), _ptr(y), _stream())
+        _call("odwscl_conv3x3_c3_f32", _ptr(x_nchw), B, H, W, _ptr(w_oihw), _ptr(bias), Cout,
+              (CONV_RELU if relu else 0) | (CONV_ROUND if round_tf32 else 0), _ptr(y), _stream())
     return y
 
 
@@ -276,6 +297,14 @@ def maxpool2x2_nhwc_bwd(x, gy, relu_mask):
     with torch.cuda.device(x.device):
         _call("odwscl_maxpool2x2_nhwc_bwd_f32", _ptr(x), _ptr(gy), B, H, W, C, int(relu_mask), _ptr(gx), _stream())
     return gx
+
+
+def round_tf32_(x):
+    """in place: x <- rna_tf32(x)"""
+    assert x.is_contiguous() and x.dtype == torch.float32
+    with torch.cuda.device(x.device):
+        _call("odwscl_split_tf32", _ptr(x), x.numel(), _ptr(x), None, _stream())
+    return x
 
 
 def split_tf32(x):

@@ -24,7 +24,13 @@
 namespace {
 
 constexpr int kBM = 128;
-enum : int { kRelu = 1, kAccum = 2, kMask = 4 };
+enum : int { kRelu = 1, kAccum = 2, kMask = 4, kRound = 8 };
+
+__device__ __forceinline__ float rna_tf32(float v) {
+  uint32_t b;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(v));
+  return __uint_as_float(b);
+}
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(192, (STAGES * (kBM + BN) * 128 + 2048 <= 110 * 1024) ? 2 : 1)
@@ -125,6 +131,7 @@ conv3x3_tf32_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
           const float4 m = __ldg(msk + j);
           o.x = m.x > 0.f ? o.x : 0.f; o.y = m.y > 0.f ? o.y : 0.f; o.z = m.z > 0.f ? o.z : 0.f; o.w = m.w > 0.f ? o.w : 0.f;
         }
+        if (flags & kRound) { o.x = rna_tf32(o.x); o.y = rna_tf32(o.y); o.z = rna_tf32(o.z); o.w = rna_tf32(o.w); }
         dst[j] = o;
       }
     }
@@ -215,7 +222,8 @@ conv3x3_c3_kernel(const float* __restrict__ x, const float* __restrict__ w, cons
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float4 o = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-      if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+      if (relu & kRelu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+      if (relu & kRound) { o.x = rna_tf32(o.x); o.y = rna_tf32(o.y); o.z = rna_tf32(o.z); o.w = rna_tf32(o.w); }
       dst[j] = o;
     }
   }
@@ -271,12 +279,9 @@ __global__ void maxpool2x2_nhwc_bwd_kernel(const float* __restrict__ x, const fl
 __global__ void split_tf32_kernel(const float* __restrict__ x, long long n, float* __restrict__ hi, float* __restrict__ lo) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float v = x[i];
-    uint32_t hb, lb;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
-    const float h = __uint_as_float(hb);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(__fsub_rn(v, h)));
+    const float h = rna_tf32(v);
     hi[i] = h;
-    lo[i] = __uint_as_float(lb);
+    if (lo != nullptr) lo[i] = rna_tf32(__fsub_rn(v, h));
   }
 }
 
@@ -334,7 +339,7 @@ ODW_API int odwscl_maxpool2x2_nhwc_bwd_f32(const float* x, const float* gy, int 
 ODW_API int odwscl_split_tf32(const float* x, long long n, float* hi, float* lo, odwscl_stream_t stream) {
   if (n < 0) return ODWSCL_EINVAL;
   if (n == 0) return 0;
-  if (!x || !hi || !lo) return ODWSCL_EINVAL;
+  if (!x || !hi) return ODWSCL_EINVAL;
   const int blocks = (int)min((long long)ODW_NUM_SMS * 16, (n + 255) / 256);
   split_tf32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, n, hi, lo);
   ODW_LAUNCH_CHECK();

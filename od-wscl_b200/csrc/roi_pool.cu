@@ -157,7 +157,7 @@ __global__ void roi_pool_fwd_generic_kernel(const float* __restrict__ feat, cons
 
 __global__ void roi_pool_bwd_kernel(const float* __restrict__ grad_out, const int32_t* __restrict__ argmax,
                                     const float* __restrict__ rois, long long total, int C, int HW, int bins,
-                                    float* __restrict__ grad_in) {
+                                    float* __restrict__ grad_in, int nhwc) {
   for (long long index = blockIdx.x * (long long)blockDim.x + threadIdx.x; index < total;
        index += (long long)gridDim.x * blockDim.x) {
     const int a = __ldcs(argmax + index);
@@ -166,7 +166,8 @@ __global__ void roi_pool_bwd_kernel(const float* __restrict__ grad_out, const in
     const int c = (int)(nc % C);
     const int n = (int)(nc / C);
     const int b = (int)__ldg(rois + (size_t)n * 5);
-    atomicAdd(grad_in + ((size_t)b * C + c) * HW + a, __ldcs(grad_out + index));
+    float* dst = nhwc ? grad_in + ((size_t)b * HW + a) * C + c : grad_in + ((size_t)b * C + c) * HW + a;
+    atomicAdd(dst, __ldcs(grad_out + index));
   }
 }
 
@@ -224,7 +225,40 @@ ODW_API int odwscl_roi_pool_bwd_f32(const float* grad_out, const int32_t* argmax
   if (!grad_out || !argmax || !rois) return ODWSCL_EINVAL;
   const long long total = (long long)R * C * ph * pw;
   const int blocks = (int)min((long long)ODW_NUM_SMS * 16, (total + 255) / 256);
-  roi_pool_bwd_kernel<<<blocks, 256, 0, st>>>(grad_out, argmax, rois, total, C, H * W, ph * pw, grad_in);
+  roi_pool_bwd_kernel<<<blocks, 256, 0, st>>>(grad_out, argmax, rois, total, C, H * W, ph * pw, grad_in, 0);
+  ODW_LAUNCH_CHECK();
+  return 0;
+}
+
+// Channels-last variants: the conv stack of this library produces / consumes NHWC maps, so the model path
+// skips the layout transpose.  feat_nhwc / grad_in_nhwc are [B,H,W,C]; out / argmax / grad_out keep the
+// reference layout [R,C,7,7] (argmax = h*W+w as always).  7x7 bins and C % 4 == 0 only.
+ODW_API int odwscl_roi_pool_fwd_nhwc_f32(const float* feat_nhwc, int B, int C, int H, int W, const float* rois, int R,
+                                         float scale, float* out, int32_t* argmax, odwscl_stream_t stream) {
+  if (B < 0 || C < 0 || H <= 0 || W <= 0 || R < 0 || (C & 3)) return ODWSCL_EINVAL;
+  if (R == 0 || C == 0) return 0;
+  if (!feat_nhwc || !rois || !out || !argmax) return ODWSCL_EINVAL;
+  const int smem = kSlab * kBins * (int)(sizeof(float) + sizeof(int));
+  ODW_CUDA(cudaFuncSetAttribute(roi_pool_fwd_nhwc7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  dim3 grid(R, odw_cdiv(C, kSlab));
+  roi_pool_fwd_nhwc7_kernel<<<grid, 7 * 32, smem, (cudaStream_t)stream>>>(feat_nhwc, rois, C, H, W, scale, out, argmax);
+  ODW_LAUNCH_CHECK();
+  return 0;
+}
+
+ODW_API int odwscl_roi_pool_bwd_nhwc_f32(const float* grad_out, const int32_t* argmax, const float* rois, int R, int B,
+                                         int C, int H, int W, float* grad_in_nhwc, odwscl_stream_t stream) {
+  if (B < 0 || C < 0 || H < 0 || W < 0 || R < 0) return ODWSCL_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t bytes = (size_t)B * C * H * W * sizeof(float);
+  if (bytes == 0) return 0;
+  if (!grad_in_nhwc) return ODWSCL_EINVAL;
+  ODW_CUDA(cudaMemsetAsync(grad_in_nhwc, 0, bytes, st));
+  if (R == 0) return 0;
+  if (!grad_out || !argmax || !rois) return ODWSCL_EINVAL;
+  const long long total = (long long)R * C * 49;
+  const int blocks = (int)min((long long)ODW_NUM_SMS * 16, (total + 255) / 256);
+  roi_pool_bwd_kernel<<<blocks, 256, 0, st>>>(grad_out, argmax, rois, total, C, H * W, 49, grad_in_nhwc, 1);
   ODW_LAUNCH_CHECK();
   return 0;
 }

@@ -7,7 +7,7 @@ from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 from torch.nn.modules.utils import _pair
 
-from . import _C
+from . import _C, capi
 
 
 class _ROIPool(Function):
@@ -16,6 +16,7 @@ class _ROIPool(Function):
         ctx.output_size = _pair(output_size)
         ctx.spatial_scale = spatial_scale
         ctx.input_shape = input.size()
+        ctx.channels_last = capi._is_nhwc(input)       # conv stack output: grad goes back in the same layout
         output, argmax = _C.roi_pool_forward(input, roi, spatial_scale, ctx.output_size[0], ctx.output_size[1])
         ctx.save_for_backward(roi, argmax)
         return output
@@ -25,8 +26,12 @@ class _ROIPool(Function):
     def backward(ctx, grad_output):
         rois, argmax = ctx.saved_tensors
         bs, ch, h, w = ctx.input_shape
-        grad_input = _C.roi_pool_backward(grad_output, None, rois, argmax, ctx.spatial_scale, ctx.output_size[0],
-                                          ctx.output_size[1], bs, ch, h, w)
+        if ctx.channels_last:
+            grad_input = capi.roi_pool_backward(grad_output, rois, argmax, ctx.output_size[0], ctx.output_size[1],
+                                                bs, ch, h, w, channels_last=True)
+        else:
+            grad_input = _C.roi_pool_backward(grad_output, None, rois, argmax, ctx.spatial_scale, ctx.output_size[0],
+                                              ctx.output_size[1], bs, ch, h, w)
         return grad_input, None, None, None
 
 

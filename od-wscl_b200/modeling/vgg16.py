@@ -7,6 +7,7 @@ import torch
 import torch.nn as nn
 
 from . import registry
+from .conv_stack import vgg_stack
 from .dropblock import DropBlock2D
 from .poolers import Pooler
 
@@ -57,8 +58,13 @@ class VGG_Base(nn.Module):
                 for p in self.features[layer].parameters():
                     p.requires_grad = False
 
+        self.strict_fp32 = False     # True: 3-pass TF32 hi/lo split in every convolution (parity tests)
+
     def forward(self, x):
-        return [self.features(x)]
+        # self.features only holds the parameters (state-dict keys backbone.body.features.{0,2,...,28});
+        # the arithmetic runs in the tcgen05 conv stack (csrc/conv3x3.cu), channels-last
+        convs = [m for m in self.features if isinstance(m, nn.Conv2d)]
+        return [vgg_stack(x, convs, strict=self.strict_fp32)]
 
 
 @registry.BACKBONES.register("VGG16-OICR")
