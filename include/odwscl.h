@@ -192,6 +192,13 @@ int odwscl_gemm_nt_tf32(const float* A, const float* B, float* C, int M, int N, 
 int odwscl_conv3x3_nhwc_tf32(const float* x, int B, int H, int W, int Cin, const float* w_krsc,
                              const float* bias, int Cout, int dilation, int flags, const float* mask_src,
                              float* y, odwscl_stream_t stream);
+/* WGRAD + bias gradient of the same convolution: dw_krsc [Cout,3,3,Cin] = sum over pixels of
+ * dz[b,h,w,co] * x[b, h+(r-1)d, w+(s-1)d, ci] (tcgen05, contraction over pixels with MN-major operands taken
+ * straight from the NHWC tensors, split over pixel ranges and combined with vector atomics; dw is zeroed
+ * inside); db [Cout] = sum over pixels of dz (may be NULL).  Cout % 32 == 0 (rows beyond Cout of the last
+ * 128-row tile are never written), Cin % 32 == 0. */
+int odwscl_conv3x3_wgrad_nhwc_tf32(const float* x, const float* dz, int B, int H, int W, int Cin, int Cout,
+                                   int dilation, float* dw_krsc, float* db, odwscl_stream_t stream);
 /* conv1_1 (Cin = 3, Cout = 64): fp32 FFMA, reads the NCHW image [B,3,H,W] and torch-layout weights
  * [64,3,3,3], writes NHWC [B,H,W,64].  `relu` is a flag mask: ODWSCL_CONV_RELU | ODWSCL_CONV_ROUND. */
 int odwscl_conv3x3_c3_f32(const float* x_nchw, int B, int H, int W, const float* w_oihw, const float* bias,

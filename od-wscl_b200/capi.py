@@ -26,7 +26,7 @@ _LAUNCHES = {
     "odwscl_discover_phase_a_f32": 2, "odwscl_discover_phase_b_f32": 1, "odwscl_bank_assemble": 1,
     "odwscl_supcon_fwd_f32": 2, "odwscl_supcon_bwd_f32": 1, "odwscl_od_layer_f32": 1,
     "odwscl_dropblock_f32": 3, "odwscl_sim_nxn_f32": 2, "odwscl_gemm_nt_tf32": 1,
-    "odwscl_conv3x3_nhwc_tf32": 1, "odwscl_conv3x3_c3_f32": 1, "odwscl_maxpool2x2_nhwc_f32": 1,
+    "odwscl_conv3x3_nhwc_tf32": 1, "odwscl_conv3x3_wgrad_nhwc_tf32": 2, "odwscl_conv3x3_c3_f32": 1, "odwscl_maxpool2x2_nhwc_f32": 1,
     "odwscl_maxpool2x2_nhwc_bwd_f32": 1, "odwscl_split_tf32": 1,
 }
 
@@ -53,6 +53,7 @@ _SIGS = {
     "odwscl_sim_nxn_f32": (_I, [_P, _I, _P, _P, _Z, _P]),
     "odwscl_gemm_nt_tf32": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "odwscl_conv3x3_nhwc_tf32": (_I, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _P, _P, _P]),
+    "odwscl_conv3x3_wgrad_nhwc_tf32": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     "odwscl_conv3x3_c3_f32": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _P]),
     "odwscl_maxpool2x2_nhwc_f32": (_I, [_P, _I, _I, _I, _I, _P, _P]),
     "odwscl_maxpool2x2_nhwc_bwd_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
@@ -268,6 +269,23 @@ def conv3x3_nhwc(x, w_krsc, bias, dilation=1, flags=0, mask_src=None, out=None):
         _call("odwscl_conv3x3_nhwc_tf32", _ptr(x), B, H, W, Cin, _ptr(w_krsc), _ptr(bias), Cout, int(dilation),
               int(flags), _ptr(mask_src), _ptr(y), _stream())
     return y
+
+
+def conv3x3_wgrad_nhwc(x, dz, dilation=1, accumulate_into=None, want_bias=True):
+    """x [B,H,W,Cin], dz [B,H,W,Cout] -> (dw_krsc [Cout,3,3,Cin], db [Cout] or None)."""
+    x, dz = _chk(x, torch.float32, "x"), _chk(dz, torch.float32, "dz")
+    B, H, W, Cin = x.shape
+    Cout = dz.shape[3]
+    assert dz.shape[:3] == x.shape[:3]
+    dw = torch.empty((Cout, 3, 3, Cin), dtype=torch.float32, device=x.device)
+    db = torch.empty((Cout,), dtype=torch.float32, device=x.device) if want_bias else None
+    with torch.cuda.device(x.device):
+        _call("odwscl_conv3x3_wgrad_nhwc_tf32", _ptr(x), _ptr(dz), B, H, W, Cin, Cout, int(dilation), _ptr(dw),
+              _ptr(db), _stream())
+    if accumulate_into is not None:
+        accumulate_into.add_(dw)
+        dw = accumulate_into
+    return dw, db
 
 
 def conv3x3_c3(x_nchw, w_oihw, bias, relu=True, round_tf32=False):

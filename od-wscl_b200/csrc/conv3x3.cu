@@ -175,6 +175,161 @@ int launch_conv(const float* x, int B, int H, int W, int Cin, const float* wk, c
 }
 
 // ---------------------------------------------------------------------------------------------
+// WGRAD: dW[co, tap, ci] = sum_pixels dZ[pixel, co] * X[pixel + tap, ci]  (one tap per CTA).
+// GEMM with the contraction over PIXELS: M = 128 output channels, N = BN input channels, K = pixels.  Both
+// operands are MN-major straight out of the NHWC tensors: a TMA box of {32 channels, 32 pixels of one image
+// row} lands as 32 rows (k = pixel) of 128 bytes (32 channels) -- eight 4-row swizzle atoms, exactly the
+// canonical MN-major SWIZZLE_128B_BASE32B layout (TMA swizzle mode 128B_ATOM_32B).  Boxes of X are fetched at the tap-shifted coordinate (zero fill =
+// padding); boxes past the row end are zero in dZ as well, so partial chunks contribute nothing.  The pixel
+// range is split across gridDim.z CTAs; partial tiles are combined with red.global.add.v4.f32 into the zeroed
+// [Cout,3,3,Cin] gradient.
+constexpr int kWgPix = 32;                                   // pixels (K) per pipeline stage
+constexpr int kWgBox = kWgPix * tc::kTileKBytes;             // bytes of one {32 ch x 32 px} box
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+conv3x3_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_constant__ CUtensorMap map_x,
+                          float* __restrict__ dw, int H, int W, int B, int Cin, int Cout, int dil, int chunks_per_cta) {
+  constexpr int A_BYTES = 4 * kWgBox, B_BYTES = (BN / 32) * kWgBox, STAGE_BYTES = A_BYTES + B_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar;
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cin_tiles = Cin / BN;
+  const int co0 = (blockIdx.x / cin_tiles) * kBM, ci0 = (blockIdx.x % cin_tiles) * BN;
+  const int tap = blockIdx.y;
+  const int r = tap / 3, q3 = tap - 3 * r;
+  const int cpr = (W + kWgPix - 1) / kWgPix;                  // chunks per image row
+  const int total_chunks = B * H * cpr;
+  const int c_begin = blockIdx.z * chunks_per_cta;
+  const int c_end = min(total_chunks, c_begin + chunks_per_cta);
+  const int kiters = max(c_end - c_begin, 0);
+
+  if (warp == 0 && tc::elect_one()) {
+    tc::tma_prefetch_desc(&map_dz);
+    tc::tma_prefetch_desc(&map_x);
+    for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+    tc::mbar_init(&tmem_full_bar, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(&tmem_base_s, BN);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  if (kiters > 0) {
+    if (warp == 0) {
+      if (tc::elect_one()) {
+        int c = c_begin;
+        int wc = c % cpr, hb = c / cpr;
+        int h = hb % H, b = hb / H;
+        for (int it = 0; it < kiters; ++it) {
+          const int s = it % STAGES;
+          tc::mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+          tc::mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+          uint8_t* a = tiles + (size_t)s * STAGE_BYTES;
+          const int w0 = wc * kWgPix;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) tc::tma_load_4d(a + j * kWgBox, &map_dz, &full_bar[s], co0 + 32 * j, w0, h, b);
+#pragma unroll
+          for (int j = 0; j < BN / 32; ++j)
+            tc::tma_load_4d(a + A_BYTES + j * kWgBox, &map_x, &full_bar[s], ci0 + 32 * j, w0 + (q3 - 1) * dil,
+                            h + (r - 1) * dil, b);
+          if (++wc == cpr) { wc = 0; if (++h == H) { h = 0; ++b; } }
+        }
+      }
+    } else if (warp == 1) {
+      if (tc::elect_one()) {
+        constexpr uint32_t idesc = tc::umma_idesc_tf32_mn(kBM, BN);
+        for (int it = 0; it < kiters; ++it) {
+          const int s = it % STAGES;
+          tc::mbar_wait(&full_bar[s], (it / STAGES) & 1);
+          tc::tc_fence_after();
+          const uint32_t a = tc::smem_u32(tiles + (size_t)s * STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < kWgPix / tc::kUmmaK; ++k) {        // 8 pixels per MMA = two 4-row (512-byte) atoms down each box
+            const uint64_t ad = tc::umma_desc_mn_sw128_32b(a + k * 1024, kWgBox, 512);
+            const uint64_t bd = tc::umma_desc_mn_sw128_32b(a + A_BYTES + k * 1024, kWgBox, 512);
+            tc::umma_tf32(tmem_base, ad, bd, idesc, (it | k) != 0);
+          }
+          tc::umma_commit(&empty_bar[s]);
+        }
+        tc::umma_commit(&tmem_full_bar);
+      }
+    } else {
+      const int q = warp & 3;
+      const int co = co0 + q * 32 + lane;
+      tc::mbar_wait(&tmem_full_bar, 0);
+      tc::tc_fence_after();
+      float v[32];
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, v);
+        tc::tmem_ld_wait();
+        if (co >= Cout) continue;
+        float* dst = dw + ((size_t)co * 9 + tap) * Cin + ci0 + c * 32;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * j), "f"(v[4 * j]), "f"(v[4 * j + 1]),
+                       "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, BN);
+}
+
+template <int BN>
+int launch_wgrad(const float* x, const float* dz, int B, int H, int W, int Cin, int Cout, int dil, float* dw, cudaStream_t st) {
+  constexpr int STAGES = 4;
+  CUtensorMap mz, mx;
+  const uint32_t box[4] = {32, (uint32_t)kWgPix, 1, 1};
+  const uint64_t dzd[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+  const uint64_t dzs[3] = {(uint64_t)Cout * 4, (uint64_t)W * Cout * 4, (uint64_t)H * W * Cout * 4};
+  int rc = tc::make_tmap_f32(&mz, dz, 4, dzd, dzs, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  if (rc) return rc;
+  const uint64_t dx[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+  const uint64_t sx[3] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4};
+  rc = tc::make_tmap_f32(&mx, x, 4, dx, sx, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  if (rc) return rc;
+  const int tiles = odw_cdiv(Cout, kBM) * (Cin / BN);
+  const int total_chunks = B * H * odw_cdiv(W, kWgPix);
+  int splits = max(1, (2 * ODW_NUM_SMS) / (tiles * 9));
+  splits = min(splits, total_chunks);
+  const int per = odw_cdiv(total_chunks, splits);
+  splits = odw_cdiv(total_chunks, per);
+  const int smem = STAGES * (4 + BN / 32) * kWgBox + 1024;
+  ODW_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_tf32_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  ODW_CUDA(cudaMemsetAsync(dw, 0, (size_t)Cout * 9 * Cin * sizeof(float), st));
+  dim3 grid(tiles, 9, splits);
+  conv3x3_wgrad_tf32_kernel<BN, STAGES><<<grid, 192, smem, st>>>(mz, mx, dw, H, W, B, Cin, Cout, dil, per);
+  ODW_LAUNCH_CHECK();
+  return 0;
+}
+
+// db[co] = sum_pixels dz[pixel, co]
+__global__ void bias_grad_kernel(const float* __restrict__ dz, long long P, int C, float* __restrict__ db) {
+  // block = 32 channels x 8 pixel lanes; grid.x = channel groups, grid.y = pixel slabs
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int py = threadIdx.x >> 5;
+  float acc = 0.f;
+  if (c < C)
+    for (long long p = (long long)blockIdx.y * 8 + py; p < P; p += (long long)gridDim.y * 8) acc += dz[p * C + c];
+  __shared__ float sm[8][33];
+  sm[py][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (py == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += sm[j][threadIdx.x & 31];
+    atomicAdd(db + c, t);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // conv1_1: Cin = 3.  thread = (pixel, 16-channel group); 4 adjacent lanes write one pixel's 64 channels.
 template <int COUT>
 __global__ void __launch_bounds__(256)
@@ -298,6 +453,30 @@ ODW_API int odwscl_conv3x3_nhwc_tf32(const float* x, int B, int H, int W, int Ci
   if (Cout % 128 == 0) return launch_conv<128, 3>(x, B, H, W, Cin, w_krsc, bias, Cout, dilation, flags, mask_src, y, st);
   if (Cout % 64 == 0) return launch_conv<64, 4>(x, B, H, W, Cin, w_krsc, bias, Cout, dilation, flags, mask_src, y, st);
   return launch_conv<32, 4>(x, B, H, W, Cin, w_krsc, bias, Cout, dilation, flags, mask_src, y, st);
+}
+
+ODW_API int odwscl_conv3x3_wgrad_nhwc_tf32(const float* x, const float* dz, int B, int H, int W, int Cin, int Cout,
+                                           int dilation, float* dw_krsc, float* db, odwscl_stream_t stream) {
+  if (B < 0 || H < 0 || W < 0 || Cin <= 0 || Cout <= 0 || (Cin % 32) || (Cout % 32) || dilation < 1) return ODWSCL_EINVAL;
+  if (!dw_krsc) return ODWSCL_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((long long)B * H * W == 0) {
+    ODW_CUDA(cudaMemsetAsync(dw_krsc, 0, (size_t)Cout * 9 * Cin * sizeof(float), st));
+    if (db) ODW_CUDA(cudaMemsetAsync(db, 0, (size_t)Cout * sizeof(float), st));
+    return 0;
+  }
+  if (!x || !dz) return ODWSCL_EINVAL;
+  if (db) {
+    ODW_CUDA(cudaMemsetAsync(db, 0, (size_t)Cout * sizeof(float), st));
+    const long long P = (long long)B * H * W;
+    dim3 grid(odw_cdiv(Cout, 32), (unsigned)min((long long)ODW_NUM_SMS * 4 / odw_cdiv(Cout, 32) + 1, (P + 7) / 8));
+    bias_grad_kernel<<<grid, 256, 0, st>>>(dz, P, Cout, db);
+    ODW_LAUNCH_CHECK();
+  }
+  if (Cin % 256 == 0) return launch_wgrad<256>(x, dz, B, H, W, Cin, Cout, dilation, dw_krsc, st);
+  if (Cin % 128 == 0) return launch_wgrad<128>(x, dz, B, H, W, Cin, Cout, dilation, dw_krsc, st);
+  if (Cin % 64 == 0) return launch_wgrad<64>(x, dz, B, H, W, Cin, Cout, dilation, dw_krsc, st);
+  return launch_wgrad<32>(x, dz, B, H, W, Cin, Cout, dilation, dw_krsc, st);
 }
 
 ODW_API int odwscl_conv3x3_c3_f32(const float* x_nchw, int B, int H, int W, const float* w_oihw, const float* bias,

@@ -84,10 +84,29 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// MN-major operand (the contraction index is the OUTER, strided one -- e.g. pixels of an NHWC tensor when the
+// GEMM contracts over pixels).  For 32-bit (tf32) data the only MN-major layout the tensor core accepts is
+// SWIZZLE_128B_BASE32B (layout type 1; "for mn-major tf32 operands, SW128_32B is the only available smem
+// layout", cutlass sm100_common.inl): 128-byte rows hold 32 consecutive M/N elements of ONE k, FOUR consecutive
+// k rows form a 512-byte atom whose 32-byte chunks are XOR-swizzled by the row index -- the image a TMA load
+// with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B produces.  LBO = byte distance between 32-element M/N groups,
+// SBO = byte distance between 4-row k groups (cute/atom/mma_traits_sm100.hpp, make_umma_desc<Major::MN>).
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128_32b(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;
+  return d;
+}
 // Instruction descriptor for kind::tf32, fp32 accumulate, both operands K-major:
 // [4,6) D format = 1 (F32), [7,10) A format = 2 (TF32), [10,13) B format = 2, [17,23) N>>3, [24,29) M>>4.
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// same, both operands MN-major ([15] a_major = 1, [16] b_major = 1)
+__host__ __device__ constexpr uint32_t umma_idesc_tf32_mn(int M, int N) {
+  return umma_idesc_tf32(M, N) | (1u << 15) | (1u << 16);
 }
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread.
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -133,7 +152,8 @@ static inline EncodeTiledFn encode_tiled_fn() {
 // fp32 tensor of rank `rank` (dims[0] innermost, contiguous), box[0] must be 32 (one 128-byte swizzle row).
 // strides_bytes[i] is the byte stride of dims[i+1].  OOB elements read as zero.
 static inline int make_tmap_f32(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
-                                const uint64_t* strides_bytes, const uint32_t* box) {
+                                const uint64_t* strides_bytes, const uint32_t* box,
+                                CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return (int)cudaErrorNotSupported;
   cuuint64_t d[5], s[4];
@@ -141,7 +161,7 @@ static inline int make_tmap_f32(CUtensorMap* map, const void* base, int rank, co
   for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, e,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
 }

@@ -6,7 +6,7 @@ kernels of csrc/conv3x3.cu, channels-last end to end, as ONE autograd node:
             NHWC buffer (channels_last strides), which the ROIPool binding consumes without a transpose.
   backward  per trainable layer: DGRAD = the same tcgen05 kernel on the flipped / transposed weights with the
             previous activation's ReLU derivative fused into its epilogue; the max-pool backward fuses the
-            same mask; WGRAD + bias gradient through csrc/conv3x3.cu when available (see `wgrad`).
+            same mask; WGRAD + bias gradient = the tcgen05 pixel-contraction kernel (see `wgrad`).
   Frozen layers (FREEZE_CONV_BODY_AT, vgg16.py:48-55) are neither differentiated nor kept alive.
 
 `strict=True` (tests) evaluates every convolution as a 3-pass TF32 hi/lo split (fp32-accurate); the default
@@ -41,15 +41,19 @@ def _conv(x, wk, bias, dil, flags, strict, mask_src=None, feeds_conv=True):
     return capi.conv3x3_nhwc(xl, wh, None, dilation=dil, flags=capi.CONV_ACCUM | flags, mask_src=mask_src, out=y)
 
 
-def wgrad(x_nhwc, dz_nhwc, w_shape, dil):
+def wgrad(x_nhwc, dz_nhwc, w_shape, dil, strict):
     """dW [Cout,Cin,3,3] and db [Cout] of one layer from its NHWC input and the NHWC gradient of its
-    pre-activation output."""
-    go = dz_nhwc.permute(0, 3, 1, 2)
-    xi = x_nhwc.permute(0, 3, 1, 2)
-    w_meta = torch.empty(w_shape, dtype=x_nhwc.dtype, device=x_nhwc.device)
-    _, dw, db = torch.ops.aten.convolution_backward(go, xi, w_meta, [w_shape[0]], [1, 1], [dil, dil], [dil, dil],
-                                                    False, [0, 0], 1, [False, True, True])
-    return dw.contiguous(), db
+    pre-activation output (tcgen05 WGRAD kernel; both operands are already TF32-rounded in single-pass mode)."""
+    if not strict:
+        dw, db = capi.conv3x3_wgrad_nhwc(x_nhwc, dz_nhwc, dilation=dil)
+    else:
+        xh, xl = capi.split_tf32(x_nhwc)
+        zh, zl = capi.split_tf32(dz_nhwc)
+        dw, _ = capi.conv3x3_wgrad_nhwc(xh, zh, dilation=dil, want_bias=False)
+        capi.conv3x3_wgrad_nhwc(xh, zl, dilation=dil, accumulate_into=dw, want_bias=False)
+        capi.conv3x3_wgrad_nhwc(xl, zh, dilation=dil, accumulate_into=dw, want_bias=False)
+        db = dz_nhwc.sum((0, 1, 2))
+    return dw.permute(0, 3, 1, 2).contiguous(), db          # [Cout,3,3,Cin] -> torch's [Cout,Cin,3,3]
 
 
 class _VGGStackFn(Function):
@@ -102,7 +106,7 @@ class _VGGStackFn(Function):
                 break
             xin = saved["in%d" % i]
             if ctx.needs_w[i]:
-                grads[2 * i], grads[2 * i + 1] = wgrad(xin, dz, ws[i].shape, dil)
+                grads[2 * i], grads[2 * i + 1] = wgrad(xin, dz, ws[i].shape, dil, ctx.strict)
             if i == ctx.first_train:
                 break
             # DGRAD: d(input of layer i).  The input is either layer i-1's post-ReLU output (mask fused in the

@@ -152,3 +152,22 @@ def test_vgg_stack_vs_torch(capi, strict):
     check(got.detach(), ref.detach(), tf.detach(), 1e-4, "feature")
     for p, a, b, t in zip(params, got_grads, ref_grads, tf_grads):
         check(a, b, t, 2e-4, tuple(p.shape))
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,dil", [
+    (1, 8, 32, 32, 32, 1), (2, 19, 27, 64, 64, 1), (1, 38, 50, 128, 256, 1), (2, 13, 70, 256, 512, 2),
+    (2, 76, 128, 512, 512, 2), (1, 20, 33, 96, 160, 1)])
+def test_conv3x3_wgrad(capi, B, H, W, Cin, Cout, dil):
+    """tcgen05 WGRAD (MN-major operands, split over pixels) + bias gradient vs torch autograd; inputs carry <= 10
+    mantissa bits so the TF32 products are exact and only fp32 accumulation order differs."""
+    g = torch.Generator().manual_seed(H * W + Cin + Cout)
+    x = q(torch.randn(B, H, W, Cin, generator=g)).cuda()
+    dz = q(torch.randn(B, H, W, Cout, generator=g)).cuda()
+    w = torch.zeros(Cout, Cin, 3, 3, device="cuda", dtype=torch.double, requires_grad=True)
+    bvec = torch.zeros(Cout, device="cuda", dtype=torch.double, requires_grad=True)
+    y = F.conv2d(x.permute(0, 3, 1, 2).double(), w, bvec, padding=dil, dilation=dil)
+    gw, gb = torch.autograd.grad(y, (w, bvec), dz.permute(0, 3, 1, 2).double())
+    dw, db = capi.conv3x3_wgrad_nhwc(x, dz, dilation=dil)
+    tol = 3e-5 * (B * H * W) ** 0.5
+    torch.testing.assert_close(dw.permute(0, 3, 1, 2), gw.float(), rtol=1e-5, atol=tol)
+    torch.testing.assert_close(db, gb.float(), rtol=1e-5, atol=tol)
