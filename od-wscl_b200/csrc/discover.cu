@@ -7,9 +7,10 @@
 // Work decomposition: a "pair" = (image b, positive class c).  Pairs are independent except for
 // the append order of the SupCon bank, which odwscl_bank_assemble reconstructs afterwards, so
 //   phase A  : 1 CTA per pair  (3 argmaxes, 3 IoU rows, union, ordered compaction, hardness)
-//   phase B  : 1 CTA per pair  (per branch: tau, similarity rows, selection rule incl. the
+//   phase B  : select: 1 CTA per (pair, branch) (tau, similarity rows, selection rule incl. the
 //              bool-vs-float quirk of loss.py:327, bitonic sort + greedy NMS sweep in shared
-//              memory, fallback, ordered set difference, membership update)
+//              memory, fallback); merge: 1 CTA per pair, branches in order (ordered set difference
+//              against the running membership, membership update)
 //   od_layer : 1 CTA per (image, branch)
 // Similarity rows are computed only for the <= |pos| query proposals the rule actually reads
 // (the reference materialises the whole N x N product per iteration, loss.py:319).
@@ -186,109 +187,130 @@ static size_t phase_b_smem_bytes(int Ncap, int L) {
   return (size_t)L * 16 + kD * 4 + (size_t)Ncap * 4 + (size_t)L * 8 + 64 * 4 + (size_t)Ncap + L;
 }
 
+// phase_b_select_kernel: grid (P, 3) -- one CTA per (pair, refinement branch).  Everything that is independent of
+// the running membership: tau, the similarity row(s), the selection rule, sort + greedy NMS -> inst[p][i].
 __global__ void __launch_bounds__(kCtaThreads, 1)
-phase_b_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ img_off, int R, int C,
-               const float* __restrict__ s0, const float* __restrict__ s1, const float* __restrict__ s2,
-               const int32_t* __restrict__ pair_img, const int32_t* __restrict__ pair_cls, int P, int Ncap,
-               int L, const float* __restrict__ F, const float* __restrict__ E,
-               const int32_t* __restrict__ amax, uint8_t* __restrict__ member,
-               const int32_t* __restrict__ offA, const int32_t* __restrict__ rowsA,
-               const float* __restrict__ colsum, float nms_thr, int32_t* __restrict__ inst,
-               int32_t* __restrict__ inst_cnt, int32_t* __restrict__ newl, int32_t* __restrict__ new_cnt,
-               float* __restrict__ hardB, float* __restrict__ tau_out, const float* __restrict__ sim_rows_in) {
+phase_b_select_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ img_off, int R, int C,
+                      const float* __restrict__ s0, const float* __restrict__ s1, const float* __restrict__ s2,
+                      const int32_t* __restrict__ pair_img, const int32_t* __restrict__ pair_cls, int P, int Ncap,
+                      int L, const float* __restrict__ F, const float* __restrict__ E,
+                      const int32_t* __restrict__ amax, const int32_t* __restrict__ offA,
+                      const int32_t* __restrict__ rowsA, float nms_thr, int32_t* __restrict__ inst,
+                      int32_t* __restrict__ inst_cnt, float* __restrict__ tau_out,
+                      const float* __restrict__ sim_rows_in) {
   extern __shared__ __align__(16) unsigned char smem[];
   const PhaseBSmem s = carve_b(smem, Ncap, L);
   __shared__ float s_v[32];
-  const int p = blockIdx.x;
+  const int p = blockIdx.x, i = blockIdx.y;
   const int b = pair_img[p], cls = pair_cls[p], col = cls + 1;
   const int off = img_off[b], N = img_off[b + 1] - off;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int K = offA[P];
-  const float cs = colsum[p];
-  uint8_t* mem = member + (size_t)p * Ncap;
   int q_lo = p, q_hi = p + 1;                      // pairs of the same image (contiguous)
   while (q_lo > 0 && pair_img[q_lo - 1] == b) --q_lo;
   while (q_hi < P && pair_img[q_hi] == b) ++q_hi;
-  const float* S[3] = {s0, s1, s2};
+  const float* Si = i == 0 ? s0 : (i == 1 ? s1 : s2);
   if (N <= 0) {
-    if (threadIdx.x < 3) { inst_cnt[p * 3 + threadIdx.x] = 0; new_cnt[p * 3 + threadIdx.x] = 0; }
+    if (threadIdx.x == 0) inst_cnt[p * 3 + i] = 0;
     return;
   }
+  const int m = amax[p * 3 + i];
+  if (threadIdx.x < kD) s.fq[threadIdx.x] = __ldg(F + (size_t)(off + m) * kD + threadIdx.x);
+  __syncthreads();
+  // ---- tau = mean_r( F[m] . coll[cls][r] )   (loss.py:320); coll = Phase-A bank of the class
+  float part = 0.f;
+  int nrows = 0;
+  for (int q = 0; q < P; ++q) {
+    if (pair_cls[q] != cls) continue;
+    const int lo = offA[q], cnt = offA[q + 1] - lo;
+    nrows += 3 * cnt;
+    for (int t = wid; t < 3 * cnt; t += nwarps) {
+      const int seg = t / cnt, k = t - seg * cnt;
+      const float* row = seg == 0 ? F + (size_t)__ldg(rowsA + lo + k) * kD
+                                  : E + (size_t)((seg - 1) * K + lo + k) * kD;
+      const float d = warp_dot128(row, s.fq, lane);
+      if (lane == 0) part += d;
+    }
+  }
+  const float tau = __fdiv_rn(cta_sum(part, s_v), (float)nrows);
+  if (threadIdx.x == 0) tau_out[p * 3 + i] = tau;
+  // ---- similarity row of m and the `>= tau` rule (loss.py:324/330)
+  for (int j = wid; j < N; j += nwarps) {
+    float sv;
+    if (sim_rows_in) sv = __ldg(sim_rows_in + (size_t)(p * 3 + i) * Ncap + j);
+    else sv = warp_dot128(F + (size_t)(off + j) * kD, s.fq, lane);
+    if (lane == 0) { s.sim[j] = sv; s.close[j] = sv >= tau ? 1 : 0; }
+  }
+  __syncthreads();
+  // ---- other positive classes of the image: close <- (float(close) >= Sim[m_n])  (loss.py:325-327)
+  for (int q = q_lo; q < q_hi; ++q) {
+    if (q == p) continue;
+    const int mn = amax[q * 3 + i];
+    if (threadIdx.x < kD) s.fq[threadIdx.x] = __ldg(F + (size_t)(off + mn) * kD + threadIdx.x);
+    __syncthreads();
+    for (int j = wid; j < N; j += nwarps) {
+      const float sn = warp_dot128(F + (size_t)(off + j) * kD, s.fq, lane);
+      if (lane == 0) s.close[j] = ((s.close[j] ? 1.f : 0.f) >= sn) ? 1 : 0;
+    }
+    __syncthreads();
+  }
+  // ---- candidates (ascending j) keyed by the class score of this branch
+  const int ncl = odw::cta_compact(
+      N, s.scan, [&](int j) { return s.close[j] != 0; },
+      [&](int k, int j) { s.key[k] = __ldg(Si + (size_t)(off + j) * C + col); s.id[k] = j; });
+  int* inst_p = inst + (size_t)(p * 3 + i) * Ncap;
+  int nk = 0;
+  if (ncl > 0) {
+    const int L2 = odw::next_pow2(ncl < 32 ? 32 : ncl);
+    for (int t = ncl + threadIdx.x; t < L2; t += blockDim.x) { s.key[t] = -INFINITY; s.id[t] = INT_MAX; }
+    for (int t = threadIdx.x; t < L2; t += blockDim.x) s.sup[t] = 0;
+    __syncthreads();
+    odw::cta_bitonic_sort(s.key, s.id, L2);
+    for (int t = threadIdx.x; t < ncl; t += blockDim.x) s.box[t] = __ldg(boxes + off + s.id[t]);
+    __syncthreads();
+    nk = odw::cta_nms_sweep(s.box, s.sup, ncl, nms_thr, 0.f,                 // loss.py:332
+                            [&](int k, int pos) { inst_p[k] = s.id[pos]; });
+  }
+  if (nk == 0) {                                                             // loss.py:333
+    if (threadIdx.x == 0) inst_p[0] = m;
+    nk = 1;
+  }
+  if (threadIdx.x == 0) inst_cnt[p * 3 + i] = nk;
+}
 
+// phase_b_merge_kernel: grid P -- the order-dependent tail, per pair, branches in sequence:
+// new = sorted(kept \ member); fallback [m]; member |= new   (loss.py:336-341)
+__global__ void __launch_bounds__(kCtaThreads, 1)
+phase_b_merge_kernel(const int32_t* __restrict__ img_off, int C, const float* __restrict__ s0,
+                     const int32_t* __restrict__ pair_img, const int32_t* __restrict__ pair_cls, int Ncap,
+                     const int32_t* __restrict__ amax, uint8_t* __restrict__ member,
+                     const float* __restrict__ colsum, const int32_t* __restrict__ inst,
+                     const int32_t* __restrict__ inst_cnt, int32_t* __restrict__ newl,
+                     int32_t* __restrict__ new_cnt, float* __restrict__ hardB) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  uint8_t* s_close = smem;                                   // [Ncap]
+  __shared__ int s_scan[64];
+  const int p = blockIdx.x;
+  const int b = pair_img[p], col = pair_cls[p] + 1;
+  const int off = img_off[b], N = img_off[b + 1] - off;
+  const float cs = colsum[p];
+  uint8_t* mem = member + (size_t)p * Ncap;
+  if (N <= 0) {
+    if (threadIdx.x < 3) new_cnt[p * 3 + threadIdx.x] = 0;
+    return;
+  }
   for (int i = 0; i < 3; ++i) {
     const int m = amax[p * 3 + i];
-    if (threadIdx.x < kD) s.fq[threadIdx.x] = __ldg(F + (size_t)(off + m) * kD + threadIdx.x);
+    const int* inst_p = inst + (size_t)(p * 3 + i) * Ncap;
+    const int nk = inst_cnt[p * 3 + i];
+    for (int j = threadIdx.x; j < N; j += blockDim.x) s_close[j] = 0;
     __syncthreads();
-    // ---- tau = mean_r( F[m] . coll[cls][r] )   (loss.py:320); coll = Phase-A bank of the class
-    float part = 0.f;
-    int nrows = 0;
-    for (int q = 0; q < P; ++q) {
-      if (pair_cls[q] != cls) continue;
-      const int lo = offA[q], cnt = offA[q + 1] - lo;
-      nrows += 3 * cnt;
-      for (int t = wid; t < 3 * cnt; t += nwarps) {
-        const int seg = t / cnt, k = t - seg * cnt;
-        const float* row = seg == 0 ? F + (size_t)__ldg(rowsA + lo + k) * kD
-                                    : E + (size_t)((seg - 1) * K + lo + k) * kD;
-        const float d = warp_dot128(row, s.fq, lane);
-        if (lane == 0) part += d;
-      }
-    }
-    const float tau = __fdiv_rn(cta_sum(part, s_v), (float)nrows);
-    if (threadIdx.x == 0) tau_out[p * 3 + i] = tau;
-    // ---- similarity row of m and the `>= tau` rule (loss.py:324/330)
-    for (int j = wid; j < N; j += nwarps) {
-      float sv;
-      if (sim_rows_in) sv = __ldg(sim_rows_in + (size_t)(p * 3 + i) * Ncap + j);
-      else sv = warp_dot128(F + (size_t)(off + j) * kD, s.fq, lane);
-      if (lane == 0) { s.sim[j] = sv; s.close[j] = sv >= tau ? 1 : 0; }
-    }
-    __syncthreads();
-    // ---- other positive classes of the image: close <- (float(close) >= Sim[m_n])  (loss.py:325-327)
-    for (int q = q_lo; q < q_hi; ++q) {
-      if (q == p) continue;
-      const int mn = amax[q * 3 + i];
-      if (threadIdx.x < kD) s.fq[threadIdx.x] = __ldg(F + (size_t)(off + mn) * kD + threadIdx.x);
-      __syncthreads();
-      for (int j = wid; j < N; j += nwarps) {
-        const float sn = warp_dot128(F + (size_t)(off + j) * kD, s.fq, lane);
-        if (lane == 0) s.close[j] = ((s.close[j] ? 1.f : 0.f) >= sn) ? 1 : 0;
-      }
-      __syncthreads();
-    }
-    // ---- candidates (ascending j) keyed by the class score of this branch
-    const float* Si = S[i];
-    const int ncl = odw::cta_compact(
-        N, s.scan, [&](int j) { return s.close[j] != 0; },
-        [&](int k, int j) { s.key[k] = __ldg(Si + (size_t)(off + j) * C + col); s.id[k] = j; });
-    int* inst_p = inst + (size_t)(p * 3 + i) * Ncap;
-    int nk = 0;
-    if (ncl > 0) {
-      const int L2 = odw::next_pow2(ncl < 32 ? 32 : ncl);
-      for (int t = ncl + threadIdx.x; t < L2; t += blockDim.x) { s.key[t] = -INFINITY; s.id[t] = INT_MAX; }
-      for (int t = threadIdx.x; t < L2; t += blockDim.x) s.sup[t] = 0;
-      __syncthreads();
-      odw::cta_bitonic_sort(s.key, s.id, L2);
-      for (int t = threadIdx.x; t < ncl; t += blockDim.x) s.box[t] = __ldg(boxes + off + s.id[t]);
-      __syncthreads();
-      nk = odw::cta_nms_sweep(s.box, s.sup, ncl, nms_thr, 0.f,                 // loss.py:332
-                              [&](int k, int pos) { inst_p[k] = s.id[pos]; });
-    }
-    if (nk == 0) {                                                             // loss.py:333
-      if (threadIdx.x == 0) inst_p[0] = m;
-      nk = 1;
-    }
-    if (threadIdx.x == 0) inst_cnt[p * 3 + i] = nk;
-    __syncthreads();
-    // ---- new = sorted(kept \ member); fallback [m]; member |= new        (loss.py:336-341)
-    for (int j = threadIdx.x; j < N; j += blockDim.x) s.close[j] = 0;
-    __syncthreads();
-    for (int k = threadIdx.x; k < nk; k += blockDim.x) s.close[inst_p[k]] = 1;
+    for (int k = threadIdx.x; k < nk; k += blockDim.x) s_close[inst_p[k]] = 1;
     __syncthreads();
     int* new_p = newl + (size_t)(p * 3 + i) * Ncap;
     float* hard_p = hardB + (size_t)(p * 3 + i) * Ncap;
     int nn = odw::cta_compact(
-        N, s.scan, [&](int j) { return s.close[j] != 0 && mem[j] == 0; },
+        N, s_scan, [&](int j) { return s_close[j] != 0 && mem[j] == 0; },
         [&](int k, int j) {
           new_p[k] = j;
           hard_p[k] = __fdiv_rn(__ldg(s0 + (size_t)(off + j) * C + col), cs);      // loss.py:343
@@ -530,10 +552,14 @@ ODW_API int odwscl_discover_phase_b_f32(const float* boxes, const int32_t* img_o
   int L = 32;
   while (L < Ncap) L <<= 1;
   const size_t smem = phase_b_smem_bytes(Ncap, L);
-  ODW_CUDA(cudaFuncSetAttribute(phase_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  phase_b_kernel<<<P, kCtaThreads, smem, (cudaStream_t)stream>>>(
+  ODW_CUDA(cudaFuncSetAttribute(phase_b_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  phase_b_select_kernel<<<dim3(P, 3), kCtaThreads, smem, (cudaStream_t)stream>>>(
       reinterpret_cast<const float4*>(boxes), img_off, R, C, s0, s1, s2, pair_img, pair_cls, P, Ncap, L, F, E,
-      amax, member, offA, rowsA, colsum, nms_thr, inst, inst_cnt, newl, new_cnt, hardB, tau_out, sim_rows_in);
+      amax, offA, rowsA, nms_thr, inst, inst_cnt, tau_out, sim_rows_in);
+  ODW_LAUNCH_CHECK();
+  phase_b_merge_kernel<<<P, kCtaThreads, Ncap, (cudaStream_t)stream>>>(img_off, C, s0, pair_img, pair_cls, Ncap, amax,
+                                                                        member, colsum, inst, inst_cnt, newl, new_cnt,
+                                                                        hardB);
   ODW_LAUNCH_CHECK();
   return 0;
 }

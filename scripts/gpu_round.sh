@@ -30,3 +30,14 @@ if [[ $ST == *n* ]]; then
       -o $OUT/prof_roipool -f python scripts/run_roipool_once.py > $OUT/ncu_full.log 2>&1
   echo "ncu full rc=$?"; ls -la $OUT
 fi
+if [[ $ST == *v* ]]; then
+  timeout 600 python scripts/bench_conv.py 2 > $OUT/bench_conv.jsonl 2>&1; echo "bench_conv rc=$?"; cat $OUT/bench_conv.jsonl
+fi
+if [[ $ST == *c* ]]; then
+  # full capture of the tcgen05 conv kernel: launches 4.. = timed conv1_2, then skip to conv4_2-shaped ones
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"conv3x3_tf32_kernel|conv3x3_wgrad" -s 3 -c 1 \
+      -o $OUT/prof_conv_a -f python scripts/bench_conv.py 2 > $OUT/ncu_conv.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"conv3x3_tf32_kernel" -s 81 -c 1 \
+      -o $OUT/prof_conv_b -f python scripts/bench_conv.py 2 >> $OUT/ncu_conv.log 2>&1
+  echo "ncu conv rc=$?"; ls -la $OUT
+fi
