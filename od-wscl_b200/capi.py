@@ -90,12 +90,41 @@ def _ptr(t):
     return c_void_p(t.data_ptr())
 
 
+# Live per-call timing (bench.py): set `profile = []` and every C-ABI call is bracketed by CUDA events recorded
+# on the stream it launches on; entries are (name, (kind, amount) or None, ev0, ev1).  `amount` is the ALGORITHMIC
+# work of the call: FLOP for the tensor-bound kernels, bytes for the HBM-bound ones.
+profile = None
+_WORK = {
+    # (x, B, H, W, Cin, w, bias, Cout, ...)
+    "odwscl_conv3x3_nhwc_tf32": lambda a: ("flop", 2.0 * a[1] * a[2] * a[3] * a[7] * 9 * a[4]),
+    # (x, dz, B, H, W, Cin, Cout, ...)
+    "odwscl_conv3x3_wgrad_nhwc_tf32": lambda a: ("flop", 2.0 * a[2] * a[3] * a[4] * a[5] * a[6] * 9),
+    # (feat, B, C, H, W, rois, R, ...): map once + rois + out + int32 argmax
+    "odwscl_roi_pool_fwd_nhwc_f32": lambda a: ("byte", 4.0 * a[1] * a[2] * a[3] * a[4] + 20.0 * a[6] + 8.0 * a[6] * a[2] * 49),
+    "odwscl_roi_pool_fwd_f32": lambda a: ("byte", 4.0 * a[1] * a[2] * a[3] * a[4] + 20.0 * a[6] + 8.0 * a[6] * a[2] * a[8] * a[9]),
+    # (grad, argmax, rois, R, B, C, H, W, ...): grad_out + argmax reads, zero + write of the map
+    "odwscl_roi_pool_bwd_nhwc_f32": lambda a: ("byte", 8.0 * a[3] * a[5] * 49 + 8.0 * a[4] * a[5] * a[6] * a[7]),
+    "odwscl_roi_pool_bwd_f32": lambda a: ("byte", 8.0 * a[3] * a[5] * a[8] * a[9] + 8.0 * a[4] * a[5] * a[6] * a[7]),
+    # (F, N, out, ...): N x N x 128 contraction
+    "odwscl_sim_nxn_f32": lambda a: ("flop", 2.0 * a[1] * a[1] * 128),
+    # (A, B, C, M, N, K, ...)
+    "odwscl_gemm_nt_tf32": lambda a: ("flop", 2.0 * a[3] * a[4] * a[5]),
+}
+
+
 def _call(name, *args):
     global launch_count
+    if profile is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = getattr(lib(), name)(*args)
     if rc != 0:
         raise RuntimeError("%s failed: %s (%d)" % (name, lib().odwscl_strerror(rc).decode(), rc))
     launch_count += _LAUNCHES.get(name, 0)
+    if profile is not None:
+        e1.record()
+        w = _WORK.get(name)
+        profile.append((name, w(args) if w else None, e0, e1))
 
 
 def _chk(t, dtype, name):

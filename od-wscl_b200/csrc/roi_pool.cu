@@ -68,14 +68,23 @@ __device__ __forceinline__ void bin_range(int p, float bsz, int start, int limit
 constexpr int kSlab = 128;            // channels per CTA in the fast path
 constexpr int kBins = 49;
 
+#define ODW_RP_CMP4(v, id)                  \
+  if (v.x > m0) { m0 = v.x; i0 = (id); }    \
+  if (v.y > m1) { m1 = v.y; i1 = (id); }    \
+  if (v.z > m2) { m2 = v.z; i2 = (id); }    \
+  if (v.w > m3) { m3 = v.w; i3 = (id); }
+
+// CQT = C/4 as a compile-time constant (cell stride becomes an immediate load offset), 0 = runtime C.
+template <int CQT>
 __global__ void __launch_bounds__(7 * 32, 4)
-roi_pool_fwd_nhwc7_kernel(const float* __restrict__ feat_nhwc, const float* __restrict__ rois, int C,
+roi_pool_fwd_nhwc7_kernel(const float4* __restrict__ feat4, const float* __restrict__ rois, int C,
                           int H, int W, float scale, float* __restrict__ out,
                           int32_t* __restrict__ argmax) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* s_val = reinterpret_cast<float*>(smem_raw);
   int* s_idx = reinterpret_cast<int*>(smem_raw + kSlab * kBins * sizeof(float));
 
+  const int CQ = CQT ? CQT : (C >> 2);
   const int n = blockIdx.x;
   const int c0 = blockIdx.y * kSlab;
   const int nch = min(kSlab, C - c0);
@@ -85,7 +94,7 @@ roi_pool_fwd_nhwc7_kernel(const float* __restrict__ feat_nhwc, const float* __re
   if (4 * lane < nch) {
     int hs, he;
     bin_range(ph, g.bh, g.y1, H, hs, he);
-    const float* base = feat_nhwc + (size_t)g.b * H * W * C + c0 + 4 * lane;
+    const float4* base = feat4 + (size_t)g.b * H * W * CQ + (c0 >> 2) + lane;
 #pragma unroll 1
     for (int pw = 0; pw < 7; ++pw) {
       int ws, we;
@@ -94,16 +103,23 @@ roi_pool_fwd_nhwc7_kernel(const float* __restrict__ feat_nhwc, const float* __re
       float m0, m1, m2, m3;
       m0 = m1 = m2 = m3 = empty ? 0.f : -FLT_MAX;
       int i0 = -1, i1 = -1, i2 = -1, i3 = -1;
-      for (int h = hs; h < he; ++h) {
-        const float* row = base + (size_t)h * W * C;
+      const int nw = we - ws;
+#pragma unroll 1
+      for (int h = hs; h < he; ++h) {          // reference scan order: rows, then columns, strict '>'
         int idx = h * W + ws;
-#pragma unroll 4
-        for (int w = ws; w < we; ++w, ++idx) {
-          const float4 v = __ldg(reinterpret_cast<const float4*>(row + (size_t)w * C));
-          if (v.x > m0) { m0 = v.x; i0 = idx; }
-          if (v.y > m1) { m1 = v.y; i1 = idx; }
-          if (v.z > m2) { m2 = v.z; i2 = idx; }
-          if (v.w > m3) { m3 = v.w; i3 = idx; }
+        const float4* p = base + (size_t)idx * CQ;
+        int k = nw;
+#pragma unroll 1
+        for (; k >= 2; k -= 2) {
+          const float4 a = __ldg(p), b = __ldg(p + CQ);
+          p += 2 * CQ;
+          ODW_RP_CMP4(a, idx);
+          ODW_RP_CMP4(b, idx + 1);
+          idx += 2;
+        }
+        if (k > 0) {
+          const float4 a = __ldg(p);
+          ODW_RP_CMP4(a, idx);
         }
       }
       const int o = (4 * lane) * kBins + ph * 7 + pw;
@@ -125,6 +141,22 @@ roi_pool_fwd_nhwc7_kernel(const float* __restrict__ feat_nhwc, const float* __re
     __stcs(o4 + i, sv4[i]);
     __stcs(a4 + i, si4[i]);
   }
+}
+
+static int launch_fwd_nhwc7(const float* nhwc, const float* rois, int C, int H, int W, int R, float scale,
+                            float* out, int32_t* argmax, cudaStream_t st) {
+  const int smem = kSlab * kBins * (int)(sizeof(float) + sizeof(int));
+  dim3 grid(R, odw_cdiv(C, kSlab));
+  const float4* f4 = reinterpret_cast<const float4*>(nhwc);
+  if (C == 512) {
+    ODW_CUDA(cudaFuncSetAttribute(roi_pool_fwd_nhwc7_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    roi_pool_fwd_nhwc7_kernel<128><<<grid, 7 * 32, smem, st>>>(f4, rois, C, H, W, scale, out, argmax);
+  } else {
+    ODW_CUDA(cudaFuncSetAttribute(roi_pool_fwd_nhwc7_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    roi_pool_fwd_nhwc7_kernel<0><<<grid, 7 * 32, smem, st>>>(f4, rois, C, H, W, scale, out, argmax);
+  }
+  ODW_LAUNCH_CHECK();
+  return 0;
 }
 
 // one thread per output scalar, NCHW direct (any bin shape / channel count)
@@ -171,6 +203,111 @@ __global__ void roi_pool_bwd_kernel(const float* __restrict__ grad_out, const in
   }
 }
 
+// ----------------------------------------------------------------------------------------
+// Backward, plane-centric: one CTA owns NCH channels of one image for a chunk of rois and accumulates the
+// scatter-add in SHARED memory (the whole H x W plane of its channels: 76*128*4ch*4 B = 152 KB), so the 49*R*C
+// scalar adds never reach L2 as atomics; grad_out / argmax are read as contiguous NCH*49-float runs per roi
+// (16-byte vector loads, streaming).  Each CTA then flushes its plane once with vector reds (NHWC:
+// red.global.add.v4.f32, one per cell) into the zeroed grad map.  Sum order differs from the reference's
+// atomicAdd order exactly as the reference's own runs differ from each other (:100-105).
+constexpr int kBwdThreads = 1024;
+constexpr int kBwdChunkRois = 512;
+
+template <int NCH, bool NHWC>
+__global__ void __launch_bounds__(kBwdThreads, 1)
+roi_pool_bwd_plane_kernel(const float* __restrict__ grad_out, const int32_t* __restrict__ argmax,
+                          const float* __restrict__ rois, int R, int C, int HW, float* __restrict__ grad_in) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* acc = reinterpret_cast<float*>(smem_raw);                         // [HW][NCH]
+  __shared__ int s_list[kBwdChunkRois];
+  __shared__ int s_n;
+  const int cg = blockIdx.x, b = blockIdx.y;
+  const int r0 = blockIdx.z * kBwdChunkRois, r1 = min(R, r0 + kBwdChunkRois);
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x)
+    if ((int)__ldg(rois + (size_t)r * 5) == b) s_list[atomicAdd(&s_n, 1)] = r;
+  __syncthreads();
+  const int nroi = s_n;
+  if (nroi == 0) return;                                                   // chunk has no roi of this image
+  {
+    float4* a4 = reinterpret_cast<float4*>(acc);
+    const int n4 = HW * NCH / 4;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = n4 * 4 + threadIdx.x; i < HW * NCH; i += blockDim.x) acc[i] = 0.f;
+  }
+  __syncthreads();
+  constexpr int kRun = NCH * 49;                                           // scalars per (roi, channel group)
+  if constexpr (NCH == 4) {
+    constexpr int kVec = kRun / 4;                                         // 49 float4 per roi
+    const int items = nroi * kVec;
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+      const int rl = it / kVec, q = it - rl * kVec;
+      const size_t off = ((size_t)s_list[rl] * C + (size_t)cg * NCH) * 49 + 4 * q;
+      const float4 g = __ldcs(reinterpret_cast<const float4*>(grad_out + off));
+      const int4 a = __ldcs(reinterpret_cast<const int4*>(argmax + off));
+      const int e = 4 * q;
+      if (a.x >= 0) atomicAdd(acc + a.x * NCH + (e) / 49, g.x);
+      if (a.y >= 0) atomicAdd(acc + a.y * NCH + (e + 1) / 49, g.y);
+      if (a.z >= 0) atomicAdd(acc + a.z * NCH + (e + 2) / 49, g.z);
+      if (a.w >= 0) atomicAdd(acc + a.w * NCH + (e + 3) / 49, g.w);
+    }
+  } else {
+    const int items = nroi * kRun;
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+      const int rl = it / kRun, e = it - rl * kRun;
+      const size_t off = ((size_t)s_list[rl] * C + (size_t)cg * NCH) * 49 + e;
+      const int a = __ldcs(argmax + off);
+      if (a >= 0) atomicAdd(acc + a * NCH + e / 49, __ldcs(grad_out + off));
+    }
+  }
+  __syncthreads();
+  if constexpr (NHWC && NCH == 4) {
+    float* dst = grad_in + (size_t)b * HW * C + (size_t)cg * NCH;
+    for (int cell = threadIdx.x; cell < HW; cell += blockDim.x) {
+      const float4 v = reinterpret_cast<const float4*>(acc)[cell];
+      if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + (size_t)cell * C), "f"(v.x), "f"(v.y),
+                     "f"(v.z), "f"(v.w)
+                     : "memory");
+    }
+  } else {
+    for (int i = threadIdx.x; i < HW * NCH; i += blockDim.x) {
+      const int ch = i / HW, cell = i - ch * HW;                           // consecutive threads -> consecutive cells
+      const float v = acc[cell * NCH + ch];
+      if (v != 0.f) {
+        float* dst = NHWC ? grad_in + ((size_t)b * HW + cell) * C + cg * NCH + ch
+                          : grad_in + ((size_t)b * C + cg * NCH + ch) * HW + cell;
+        atomicAdd(dst, v);
+      }
+    }
+  }
+}
+
+template <int NCH, bool NHWC>
+static int launch_bwd_plane(const float* grad_out, const int32_t* argmax, const float* rois, int R, int B, int C,
+                            int HW, float* grad_in, cudaStream_t st) {
+  const int smem = HW * NCH * (int)sizeof(float);
+  ODW_CUDA(cudaFuncSetAttribute(roi_pool_bwd_plane_kernel<NCH, NHWC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  dim3 grid(C / NCH, B, odw_cdiv(R, kBwdChunkRois));
+  roi_pool_bwd_plane_kernel<NCH, NHWC><<<grid, kBwdThreads, smem, st>>>(grad_out, argmax, rois, R, C, HW, grad_in);
+  ODW_LAUNCH_CHECK();
+  return 0;
+}
+
+// picks the widest channel group whose plane fits in shared memory; false = no plane-centric path (7x7 only)
+template <bool NHWC>
+static int bwd_plane_dispatch(const float* grad_out, const int32_t* argmax, const float* rois, int R, int B, int C,
+                              int HW, float* grad_in, cudaStream_t st, bool* done) {
+  const size_t kMaxSmem = 220 * 1024;
+  *done = true;
+  if (C % 4 == 0 && (size_t)HW * 16 <= kMaxSmem) return launch_bwd_plane<4, NHWC>(grad_out, argmax, rois, R, B, C, HW, grad_in, st);
+  if (C % 2 == 0 && (size_t)HW * 8 <= kMaxSmem) return launch_bwd_plane<2, NHWC>(grad_out, argmax, rois, R, B, C, HW, grad_in, st);
+  if ((size_t)HW * 4 <= kMaxSmem) return launch_bwd_plane<1, NHWC>(grad_out, argmax, rois, R, B, C, HW, grad_in, st);
+  *done = false;
+  return 0;
+}
+
 }  // namespace
 
 ODW_API size_t odwscl_roi_pool_fwd_ws_bytes(int B, int C, int H, int W, int R, int ph, int pw) {
@@ -194,16 +331,7 @@ ODW_API int odwscl_roi_pool_fwd_f32(const float* feat, int B, int C, int H, int 
     dim3 tg(odw_cdiv(HW, 32), odw_cdiv(C, 32), B);
     nchw_to_nhwc_kernel<<<tg, dim3(32, 8), 0, st>>>(feat, nhwc, C, HW);
     ODW_LAUNCH_CHECK();
-    const int smem = kSlab * kBins * (int)(sizeof(float) + sizeof(int));
-    static bool attr_set = false;   // idempotent; benign if raced
-    if (!attr_set) {
-      ODW_CUDA(cudaFuncSetAttribute(roi_pool_fwd_nhwc7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      attr_set = true;
-    }
-    dim3 grid(R, odw_cdiv(C, kSlab));
-    roi_pool_fwd_nhwc7_kernel<<<grid, 7 * 32, smem, st>>>(nhwc, rois, C, H, W, scale, out, argmax);
-    ODW_LAUNCH_CHECK();
-    return 0;
+    return launch_fwd_nhwc7(nhwc, rois, C, H, W, R, scale, out, argmax, st);
   }
   const long long total = (long long)R * C * ph * pw;
   const int blocks = (int)min((long long)ODW_NUM_SMS * 16, (total + 255) / 256);
@@ -223,6 +351,11 @@ ODW_API int odwscl_roi_pool_bwd_f32(const float* grad_out, const int32_t* argmax
   ODW_CUDA(cudaMemsetAsync(grad_in, 0, bytes, st));
   if (R == 0) return 0;
   if (!grad_out || !argmax || !rois) return ODWSCL_EINVAL;
+  if (ph == 7 && pw == 7) {
+    bool done = false;
+    const int rc = bwd_plane_dispatch<false>(grad_out, argmax, rois, R, B, C, H * W, grad_in, st, &done);
+    if (rc != 0 || done) return rc;
+  }
   const long long total = (long long)R * C * ph * pw;
   const int blocks = (int)min((long long)ODW_NUM_SMS * 16, (total + 255) / 256);
   roi_pool_bwd_kernel<<<blocks, 256, 0, st>>>(grad_out, argmax, rois, total, C, H * W, ph * pw, grad_in, 0);
@@ -238,12 +371,7 @@ ODW_API int odwscl_roi_pool_fwd_nhwc_f32(const float* feat_nhwc, int B, int C, i
   if (B < 0 || C < 0 || H <= 0 || W <= 0 || R < 0 || (C & 3)) return ODWSCL_EINVAL;
   if (R == 0 || C == 0) return 0;
   if (!feat_nhwc || !rois || !out || !argmax) return ODWSCL_EINVAL;
-  const int smem = kSlab * kBins * (int)(sizeof(float) + sizeof(int));
-  ODW_CUDA(cudaFuncSetAttribute(roi_pool_fwd_nhwc7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  dim3 grid(R, odw_cdiv(C, kSlab));
-  roi_pool_fwd_nhwc7_kernel<<<grid, 7 * 32, smem, (cudaStream_t)stream>>>(feat_nhwc, rois, C, H, W, scale, out, argmax);
-  ODW_LAUNCH_CHECK();
-  return 0;
+  return launch_fwd_nhwc7(feat_nhwc, rois, C, H, W, R, scale, out, argmax, (cudaStream_t)stream);
 }
 
 ODW_API int odwscl_roi_pool_bwd_nhwc_f32(const float* grad_out, const int32_t* argmax, const float* rois, int R, int B,
@@ -256,6 +384,11 @@ ODW_API int odwscl_roi_pool_bwd_nhwc_f32(const float* grad_out, const int32_t* a
   ODW_CUDA(cudaMemsetAsync(grad_in_nhwc, 0, bytes, st));
   if (R == 0) return 0;
   if (!grad_out || !argmax || !rois) return ODWSCL_EINVAL;
+  {
+    bool done = false;
+    const int rc = bwd_plane_dispatch<true>(grad_out, argmax, rois, R, B, C, H * W, grad_in_nhwc, st, &done);
+    if (rc != 0 || done) return rc;
+  }
   const long long total = (long long)R * C * 49;
   const int blocks = (int)min((long long)ODW_NUM_SMS * 16, (total + 255) / 256);
   roi_pool_bwd_kernel<<<blocks, 256, 0, st>>>(grad_out, argmax, rois, total, C, H * W, 49, grad_in_nhwc, 1);

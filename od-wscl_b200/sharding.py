@@ -1,0 +1,56 @@
+"""Multi-GPU host logic of the hot path: images shard across ranks, the rank-local contrastive bank
+stays local (modeling/roi_heads/weak_head/loss.py:276-347 only sees the rank's own targets/proposals), and the one
+exchange per step is the gradient all-reduce (tools/train_net.py:50-55).  One process per GPU; `torch.distributed`
+(NCCL on the GPU box, gloo in the CPU tests) is the plumbing."""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def env_world():
+    """(world_size, rank, local_rank) as torchrun exports them."""
+    return (int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")),
+            int(os.environ.get("LOCAL_RANK", "0")))
+
+
+def images_per_gpu(ims_per_batch, world):
+    """data/build.py:150-155: the global batch must divide evenly over the ranks."""
+    if ims_per_batch % world != 0:
+        raise ValueError("SOLVER.IMS_PER_BATCH (%d) must be divisible by the number of GPUs (%d) used."
+                         % (ims_per_batch, world))
+    return ims_per_batch // world
+
+
+def shard_image_ids(ims_per_batch, world, rank):
+    """Global image indices of one step that rank `rank` owns (contiguous block, as the reference's
+    DistributedSampler + BatchSampler hand them out per iteration)."""
+    per = images_per_gpu(ims_per_batch, world)
+    return list(range(rank * per, (rank + 1) * per))
+
+
+def rank_seed(base, rank, images_per_rank):
+    """synth_batch seeds image i of a rank with seed+i: give every rank a disjoint seed range so the global batch
+    of a step is the same set of images for any world size."""
+    return base + rank * images_per_rank
+
+
+def wrap_ddp(model, device=None):
+    """DDP exactly as the reference wraps it (tools/train_net.py:50-55: broadcast_buffers=False), with
+    static_graph instead of find_unused_parameters -- every parameter receives a gradient on this path."""
+    ids = [device.index] if device is not None and device.type == "cuda" else None
+    return torch.nn.parallel.DistributedDataParallel(model, device_ids=ids, broadcast_buffers=False,
+                                                     static_graph=True)
+
+
+def max_over_ranks(value, device):
+    """Bench timing rule: the slowest rank's device time is the step time."""
+    t = torch.tensor([float(value)], device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def proposals_per_step(world, images_per_rank, proposals_per_image):
+    """Units all ranks process in one step (weak scaling: per-rank work is fixed)."""
+    return world * images_per_rank * proposals_per_image

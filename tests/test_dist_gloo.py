@@ -1,0 +1,104 @@
+"""N>1 host logic on CPU: world_size-2 gloo processes.  The path shards by image with no collective
+in the forward math; the one exchange is the gradient all-reduce (mean), checked here against a single-process
+run over the union of the shards."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _make_head():
+    from odwscl_b200.config import cfg
+    from odwscl_b200.modeling.predictors import MISTPredictor
+    torch.manual_seed(0)
+    m = MISTPredictor(cfg, 64)
+    for p in m.parameters():                      # the reference init (std 1e-3) makes every gradient tiny
+        torch.nn.init.normal_(p, std=0.05)
+    return m
+
+
+def _shard_inputs(image_ids, n=48):
+    from odwscl_b200.synth import synth_batch
+    xs, props = [], []
+    for i in image_ids:
+        _, _, boxes, _ = synth_batch(1, n, 320, 256, seed=1234 + i)
+        g = torch.Generator().manual_seed(77 + i)
+        xs.append(torch.randn(n, 64, generator=g))
+        props.append(boxes[0])
+    return torch.cat(xs), props
+
+
+def _loss(model, x, props):
+    cls, det, refs, bbs = model(x, props)
+    per_img = []
+    for c, d in zip(cls.split([len(p) for p in props]), det.split([len(p) for p in props])):
+        s = (torch.softmax(c, 1) * torch.softmax(d, 0)).sum(0).clamp(1e-6, 1 - 1e-6)     # loss.py:349-354 (MIL)
+        per_img.append(-(torch.log(1 - s)).mean())
+    return torch.stack(per_img).mean() + sum(r.square().mean() for r in refs) + sum(b.square().mean() for b in bbs)
+
+
+def _worker(rank, world, port, ims_per_batch, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE=str(world), RANK=str(rank),
+                      LOCAL_RANK=str(rank))
+    from odwscl_b200 import sharding
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        assert sharding.env_world() == (world, rank, rank)
+        ids = sharding.shard_image_ids(ims_per_batch, world, rank)
+        model = _make_head()
+        ddp = sharding.wrap_ddp(model)
+        x, props = _shard_inputs(ids)
+        _loss(ddp, x, props).backward()
+        grads = {k: p.grad.clone() for k, p in model.named_parameters()}
+        slow = sharding.max_over_ranks(10.0 + rank, torch.device("cpu"))
+        if rank == 0:
+            torch.save({"grads": grads, "ids": ids, "slow": slow}, out)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_gradient_allreduce_matches_single_process(tmp_path):
+    sys.path.insert(0, ROOT)
+    from odwscl_b200 import sharding
+    world, ims = 2, 4
+    out = str(tmp_path / "rank0.pt")
+    mp.start_processes(_worker, args=(world, _free_port(), ims, out), nprocs=world, join=True, start_method="spawn")
+    got = torch.load(out)
+    assert got["ids"] == [0, 1] and got["slow"] == 11.0
+    # single process: mean over ranks of the per-rank losses == DDP's averaged gradient
+    model = _make_head()
+    total = 0
+    for r in range(world):
+        x, props = _shard_inputs(sharding.shard_image_ids(ims, world, r))
+        total = total + _loss(model, x, props) / world
+    total.backward()
+    for k, p in model.named_parameters():
+        torch.testing.assert_close(got["grads"][k], p.grad, rtol=1e-5, atol=1e-7)
+
+
+def test_sharding_rules():
+    from odwscl_b200 import sharding
+    assert sharding.images_per_gpu(8, 4) == 2
+    with pytest.raises(ValueError):
+        sharding.images_per_gpu(8, 3)                      # data/build.py:150-155
+    ids = [sharding.shard_image_ids(8, 4, r) for r in range(4)]
+    assert sorted(sum(ids, [])) == list(range(8))
+    assert sharding.rank_seed(1234, 3, 2) == 1240
+    assert sharding.proposals_per_step(8, 2, 2000) == 32000

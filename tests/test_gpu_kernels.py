@@ -106,6 +106,31 @@ def test_roi_pool_full_size_properties(capi):
     # linearity of the backward in grad_out
     gi2 = capi.roi_pool_backward(2.0 * go, rois, arg, 7, 7, B, C, H, W)
     torch.testing.assert_close(gi2, 2.0 * gi, rtol=1e-4, atol=1e-3)
+    # the reference's own scatter-add arithmetic (torchvision kernel, same lineage) at full size
+    tv_gi = torch.ops.torchvision._roi_pool_backward(go, rois, tv_arg, 0.125, 7, 7, B, C, H, W)
+    torch.testing.assert_close(gi, tv_gi, rtol=1e-4, atol=1e-3)
+    # channels-last entry points (what the conv stack feeds): identical forward, same backward
+    feat_cl = feat.contiguous(memory_format=torch.channels_last)
+    out_cl, arg_cl = capi.roi_pool_forward(feat_cl, rois, 0.125, 7, 7)
+    assert torch.equal(out_cl, out) and torch.equal(arg_cl, arg)
+    gi_cl = capi.roi_pool_backward(go, rois, arg, 7, 7, B, C, H, W, channels_last=True)
+    assert gi_cl.shape == gi.shape
+    torch.testing.assert_close(gi_cl.contiguous(), gi, rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("B,C,H,W,R", [(2, 6, 152, 200, 300), (1, 5, 160, 250, 64), (3, 16, 30, 40, 1500)])
+def test_roi_pool_bwd_plane_variants(capi, B, C, H, W, R):
+    """Backward plane kernel with 2 / 1 channels per CTA (large maps, odd C) and several roi chunks per image."""
+    g = torch.Generator().manual_seed(C * 7 + R)
+    feat = torch.randn(B, C, H, W, generator=g)
+    rois = _rand_rois(g, B, H, W, R)
+    out, arg = capi.roi_pool_forward(feat.cuda(), rois.cuda(), 0.125, 7, 7)
+    eo, ea = orc.roi_pool_forward(feat.numpy(), rois.numpy(), 0.125, 7, 7)
+    assert np.array_equal(out.cpu().numpy(), eo) and np.array_equal(arg.cpu().numpy(), ea)
+    go = torch.randint(-8, 9, out.shape, generator=g).float() / 4        # exactly representable sums: bit-exact
+    gi = capi.roi_pool_backward(go.cuda(), rois.cuda(), arg, 7, 7, B, C, H, W)
+    egi = orc.roi_pool_backward(go.numpy(), ea, rois.numpy(), B, C, H, W)
+    assert np.array_equal(gi.cpu().numpy(), egi)
 
 
 # ------------------------------------------------------------------------------- ROIAlign
