@@ -160,6 +160,12 @@ int odwscl_od_layer_f32(const float* boxes, const int32_t* img_off, int B, int R
 int odwscl_dropblock_f32(const float* x, const float* centres, int R, int C, int ph, int pw,
                          int block, float* y, float* scale_io, int reuse_scale,
                          odwscl_stream_t stream);
+/* Same over a PADDED batch: only the first *n_valid_dev rows (a device-resident count, <= R) take part in the
+ * renormalisation and are written; rows past it are zero-filled.  Lets the caller size the batch from an upper
+ * bound without reading the count back (no host synchronisation in the contrastive branch, loss.py:299-310). */
+int odwscl_dropblock_rows_f32(const float* x, const float* centres, int R, int C, int ph, int pw,
+                              int block, float* y, float* scale_io, int reuse_scale,
+                              const int32_t* n_valid_dev, odwscl_stream_t stream);
 
 /* ---- A11 (drop-in for loss.py:319): full N x N similarity F F^T on the tensor cores
  * (tcgen05.mma kind::tf32 fed by TMA, accumulators in TMEM; 3xTF32 operand split so the result is

@@ -25,7 +25,7 @@ _LAUNCHES = {
     "odwscl_roi_align_bwd_f32": 1, "odwscl_box_iou_f32": 1, "odwscl_nms_f32": 1, "odwscl_nms_legacy_f32": 1,
     "odwscl_discover_phase_a_f32": 2, "odwscl_discover_phase_b_f32": 2, "odwscl_bank_assemble": 1,
     "odwscl_supcon_fwd_f32": 2, "odwscl_supcon_bwd_f32": 1, "odwscl_od_layer_f32": 1,
-    "odwscl_dropblock_f32": 3, "odwscl_sim_nxn_f32": 2, "odwscl_gemm_nt_tf32": 1,
+    "odwscl_dropblock_f32": 3, "odwscl_dropblock_rows_f32": 3, "odwscl_sim_nxn_f32": 2, "odwscl_gemm_nt_tf32": 1,
     "odwscl_conv3x3_nhwc_tf32": 1, "odwscl_conv3x3_wgrad_nhwc_tf32": 2, "odwscl_conv3x3_c3_f32": 1, "odwscl_maxpool2x2_nhwc_f32": 1,
     "odwscl_maxpool2x2_nhwc_bwd_f32": 1, "odwscl_split_tf32": 1,
 }
@@ -49,6 +49,7 @@ _SIGS = {
     "odwscl_supcon_bwd_f32": (_I, [_P, _P, _I, _P, _P, _P, _P, _I, _F, _P, _P, _P, _P, _P]),
     "odwscl_od_layer_f32": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _I, _P, _P, _F, _P, _P, _P, _P]),
     "odwscl_dropblock_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P]),
+    "odwscl_dropblock_rows_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P]),
     "odwscl_sim_nxn_ws_bytes": (_Z, [_I]),
     "odwscl_sim_nxn_f32": (_I, [_P, _I, _P, _P, _Z, _P]),
     "odwscl_gemm_nt_tf32": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
@@ -265,8 +266,9 @@ def gemm_nt_tf32(A, B):
     return C
 
 
-def dropblock(x, centres, block, scale_io=None):
-    """y = x * block_mask * numel/sum.  Pass the returned scale_io back in for the backward."""
+def dropblock(x, centres, block, scale_io=None, n_valid=None):
+    """y = x * block_mask * numel/sum.  Pass the returned scale_io back in for the backward.  `n_valid` (int32 device
+    tensor [1]) restricts the renormalisation and the output to the first n_valid rows of a padded batch."""
     x, centres = _chk(x, torch.float32, "x"), _chk(centres, torch.float32, "centres")
     R, C, ph, pw = x.shape
     y = torch.empty_like(x)
@@ -274,8 +276,12 @@ def dropblock(x, centres, block, scale_io=None):
     if scale_io is None:
         scale_io = torch.empty((2,), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
-        _call("odwscl_dropblock_f32", _ptr(x), _ptr(centres), R, C, ph, pw, int(block), _ptr(y), _ptr(scale_io),
-              int(reuse), _stream())
+        if n_valid is None:
+            _call("odwscl_dropblock_f32", _ptr(x), _ptr(centres), R, C, ph, pw, int(block), _ptr(y), _ptr(scale_io),
+                  int(reuse), _stream())
+        else:
+            _call("odwscl_dropblock_rows_f32", _ptr(x), _ptr(centres), R, C, ph, pw, int(block), _ptr(y),
+                  _ptr(scale_io), int(reuse), _ptr(_chk(n_valid, torch.int32, "n_valid")), _stream())
     return y, scale_io
 
 

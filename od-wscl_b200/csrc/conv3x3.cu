@@ -18,6 +18,8 @@
 //
 // Reference arithmetic: cuDNN through torch.nn.Conv2d; TF32 is what torch 1.7.1 (the reference's pin,
 // README.md:23) runs by default on tensor-core GPUs.  Single-pass mode = TF32 inputs / fp32 accumulate.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_sm100.cuh"
 
@@ -32,18 +34,168 @@ __device__ __forceinline__ float rna_tf32(float v) {
   return __uint_as_float(b);
 }
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(192, (STAGES * (kBM + BN) * 128 + 2048 <= 110 * 1024) ? 2 : 1)
+// MT = 128-pixel tiles per CTA (1 or 2).  With MT = 2 the CTA keeps two accumulators in TMEM and feeds both from the
+// SAME weight tile in shared memory: the operand bytes an SM has to ingest per FLOP drop by a third for BN = 256
+// (64 KB per 2x work instead of 48 KB), which is what bounds the Cout >= 256 layers (measured ~58 B/clk/SM).
+// CL = thread-block cluster size along the pixel-tile axis (1 or 2): the CL CTAs of a cluster load 1/CL of the
+// weight tile each and TMA-multicast it to all of them.  Measured neutral-to-slower on B200 (the limiter is the
+// per-SM ingest rate, not aggregate L2 bandwidth), so it is off unless ODWSCL_CONV_CLUSTER=2.
+template <int BN, int STAGES, int CL, int MT>
+__global__ void __launch_bounds__(192, (STAGES * (MT * kBM + BN) * 128 + 2048 <= 110 * 1024) ? 2 : 1)
 conv3x3_tf32_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                     const float* __restrict__ bias, const float* __restrict__ mask_src, float* __restrict__ y,
-                    int H, int W, int Cin, int Cout, int tw_log2, int tiles_w, int tiles_h, int dil, int flags) {
-  constexpr int A_BYTES = kBM * tc::kTileKBytes, B_BYTES = BN * tc::kTileKBytes, STAGE_BYTES = A_BYTES + B_BYTES;
+                    int H, int W, int Cin, int Cout, int tw_log2, int tiles_w, int tiles_h, int total_tiles, int dil,
+                    int flags) {
+  constexpr int A_TILE = kBM * tc::kTileKBytes, A_BYTES = MT * A_TILE, B_BYTES = BN * tc::kTileKBytes;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static_assert(MT * BN <= 512, "accumulators exceed the 512 TMEM columns");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar;
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int TW = 1 << tw_log2, TH = kBM >> tw_log2;
+  int tb[MT], th0[MT], tw0[MT];
+#pragma unroll
+  for (int m = 0; m < MT; ++m) {
+    int t = blockIdx.x * MT + m;               // tiles past the end decode to b >= B: TMA zero-fills, epilogue skips
+    const int tx = t % tiles_w; t /= tiles_w;
+    const int ty = t % tiles_h;
+    tb[m] = t / tiles_h;
+    tw0[m] = tx * TW;
+    th0[m] = ty * TH;
+  }
+  const int n0 = blockIdx.y * BN;
+  const int cchunks = Cin / tc::kTileK;
+  const int kiters = 9 * cchunks;
+
+  if (warp == 0 && tc::elect_one()) {
+    tc::tma_prefetch_desc(&map_x);
+    tc::tma_prefetch_desc(&map_w);
+    for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], CL); }
+    tc::mbar_init(&tmem_full_bar, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(&tmem_base_s, MT * BN);
+  tc::tc_fence_before();
+  __syncthreads();
+  if (CL > 1) tc::cluster_sync_all();          // peers' barriers are initialised before anything is multicast at them
+  tc::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t crank = CL > 1 ? tc::cluster_ctarank() : 0;
+  constexpr uint16_t kCtaMask = (uint16_t)((1u << CL) - 1);
+
+  if (warp == 0) {
+    if (tc::elect_one()) {
+      int tap = 0, cc = 0;
+      for (int it = 0; it < kiters; ++it) {
+        const int s = it % STAGES;
+        tc::mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+        tc::mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+        uint8_t* a = tiles + (size_t)s * STAGE_BYTES;
+        const int r = tap / 3, q = tap - 3 * r;
+        // input patch shifted by the tap; rows / columns outside the image arrive as zeros (= padding)
+#pragma unroll
+        for (int m = 0; m < MT; ++m)
+          tc::tma_load_4d(a + m * A_TILE, &map_x, &full_bar[s], cc * tc::kTileK, tw0[m] + (q - 1) * dil,
+                          th0[m] + (r - 1) * dil, tb[m]);
+        if (CL == 1)
+          tc::tma_load_2d(a + A_BYTES, &map_w, &full_bar[s], tap * Cin + cc * tc::kTileK, n0);
+        else      // my 1/CL of the weight rows, delivered to every CTA of the cluster (each expects the whole tile)
+          tc::tma_load_2d_mc(a + A_BYTES + crank * (B_BYTES / CL), &map_w, &full_bar[s], tap * Cin + cc * tc::kTileK,
+                             n0 + (int)crank * (BN / CL), kCtaMask);
+        if (++cc == cchunks) { cc = 0; ++tap; }
+      }
+    }
+  } else if (warp == 1) {
+    if (tc::elect_one()) {
+      constexpr uint32_t idesc = tc::umma_idesc_tf32(kBM, BN);
+      for (int it = 0; it < kiters; ++it) {
+        const int s = it % STAGES;
+        tc::mbar_wait(&full_bar[s], (it / STAGES) & 1);
+        tc::tc_fence_after();
+        const uint32_t a = tc::smem_u32(tiles + (size_t)s * STAGE_BYTES);
+        const uint64_t bd = tc::umma_desc_sw128(a + A_BYTES);
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+          const uint64_t ad = tc::umma_desc_sw128(a + m * A_TILE);
+#pragma unroll
+          for (int k = 0; k < tc::kTileK / tc::kUmmaK; ++k)
+            tc::umma_tf32(tmem_base + m * BN, ad + 2 * k, bd + 2 * k, idesc, (it | k) != 0);
+        }
+        if (CL == 1) tc::umma_commit(&empty_bar[s]);
+        else tc::umma_commit_mc(&empty_bar[s], kCtaMask);  // the stage is refilled by multicast: free it in every CTA
+      }
+      tc::umma_commit(&tmem_full_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    tc::mbar_wait(&tmem_full_bar, 0);
+    tc::tc_fence_after();
+    float v[32];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      const int h = th0[m] + (row >> tw_log2), w = tw0[m] + (row & (TW - 1));
+      const bool valid = (h < H) && (w < W) && (blockIdx.x * MT + m < total_tiles);
+      const size_t pix = ((size_t)tb[m] * H + h) * W + w;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + m * BN + c * 32, v);
+        tc::tmem_ld_wait();
+        const int co = n0 + c * 32;
+        if (!valid || co >= Cout) continue;
+        float4* dst = reinterpret_cast<float4*>(y + pix * Cout + co);
+        const float4* msk = reinterpret_cast<const float4*>(mask_src + pix * Cout + co);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          if (bias != nullptr) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + co) + j);
+            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+          }
+          if (flags & kAccum) {
+            const float4 p = dst[j];
+            o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+          }
+          if (flags & kRelu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          if (flags & kMask) {
+            const float4 mm = __ldg(msk + j);
+            o.x = mm.x > 0.f ? o.x : 0.f; o.y = mm.y > 0.f ? o.y : 0.f; o.z = mm.z > 0.f ? o.z : 0.f; o.w = mm.w > 0.f ? o.w : 0.f;
+          }
+          if (flags & kRound) { o.x = rna_tf32(o.x); o.y = rna_tf32(o.y); o.z = rna_tf32(o.z); o.w = rna_tf32(o.w); }
+          dst[j] = o;
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (CL > 1) tc::cluster_sync_all();          // no CTA leaves while a peer can still arrive on its barriers
+  if (warp == 1) tc::tmem_dealloc(tmem_base, MT * BN);
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair version for Cout % 256 == 0 (tcgen05 cta_group::2).  A single-CTA 128 x 256 TF32 tile is bound by the
+// SM's shared-memory bandwidth: per K = 8 step the tensor core reads 12 KB of operands and TMA writes the same 12 KB,
+// 176 B/clk against the 128 B/clk an SM has (measured: tensor pipe 73 % busy = 128/176).  Two CTAs of a cluster own
+// adjacent pixel tiles and ONE 256-channel weight tile: each stages its own A tile and HALF of the B tile, the leader
+// CTA issues M = 256 MMAs that read both halves, and each SM's shared-memory traffic drops to 115 B/clk.
+template <int STAGES>
+__global__ void __launch_bounds__(192, 1)
+conv3x3_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                         const float* __restrict__ bias, const float* __restrict__ mask_src, float* __restrict__ y,
+                         int H, int W, int Cin, int Cout, int tw_log2, int tiles_w, int tiles_h, int dil, int flags) {
+  constexpr int BN = 256, A_BYTES = kBM * tc::kTileKBytes, B_BYTES = (BN / 2) * tc::kTileKBytes;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar;
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = tc::cluster_ctarank();
   const int TW = 1 << tw_log2, TH = kBM >> tw_log2;
   int t = blockIdx.x;
   const int tx = t % tiles_w; t /= tiles_w;
@@ -61,9 +213,10 @@ conv3x3_tf32_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     tc::mbar_init(&tmem_full_bar, 1);
     tc::fence_barrier_init();
   }
-  if (warp == 1) tc::tmem_alloc(&tmem_base_s, BN);
+  if (warp == 1) tc::tmem_alloc_2sm(&tmem_base_s, BN);
   tc::tc_fence_before();
   __syncthreads();
+  tc::cluster_sync_all();                      // both CTAs' barriers exist before any TMA / commit targets them
   tc::tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
@@ -73,18 +226,18 @@ conv3x3_tf32_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       for (int it = 0; it < kiters; ++it) {
         const int s = it % STAGES;
         tc::mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
-        tc::mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+        // the leader's barrier collects the bytes of BOTH CTAs (each TMA below signals it through the peer-bit mask)
+        if (crank == 0) tc::mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
         uint8_t* a = tiles + (size_t)s * STAGE_BYTES;
         const int r = tap / 3, q = tap - 3 * r;
-        // input patch shifted by the tap; rows / columns outside the image arrive as zeros (= padding)
-        tc::tma_load_4d(a, &map_x, &full_bar[s], cc * tc::kTileK, w0 + (q - 1) * dil, h0 + (r - 1) * dil, b);
-        tc::tma_load_2d(a + A_BYTES, &map_w, &full_bar[s], tap * Cin + cc * tc::kTileK, n0);
+        tc::tma_load_4d_2sm(a, &map_x, &full_bar[s], cc * tc::kTileK, w0 + (q - 1) * dil, h0 + (r - 1) * dil, b);
+        tc::tma_load_2d_2sm(a + A_BYTES, &map_w, &full_bar[s], tap * Cin + cc * tc::kTileK, n0 + (int)crank * (BN / 2));
         if (++cc == cchunks) { cc = 0; ++tap; }
       }
     }
   } else if (warp == 1) {
-    if (tc::elect_one()) {
-      constexpr uint32_t idesc = tc::umma_idesc_tf32(kBM, BN);
+    if (crank == 0 && tc::elect_one()) {
+      constexpr uint32_t idesc = tc::umma_idesc_tf32(2 * kBM, BN);
       for (int it = 0; it < kiters; ++it) {
         const int s = it % STAGES;
         tc::mbar_wait(&full_bar[s], (it / STAGES) & 1);
@@ -93,10 +246,10 @@ conv3x3_tf32_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         const uint64_t ad = tc::umma_desc_sw128(a), bd = tc::umma_desc_sw128(a + A_BYTES);
 #pragma unroll
         for (int k = 0; k < tc::kTileK / tc::kUmmaK; ++k)
-          tc::umma_tf32(tmem_base, ad + 2 * k, bd + 2 * k, idesc, (it | k) != 0);
-        tc::umma_commit(&empty_bar[s]);
+          tc::umma_tf32_2sm(tmem_base, ad + 2 * k, bd + 2 * k, idesc, (it | k) != 0);
+        tc::umma_commit_2sm_mc(&empty_bar[s], 3);          // the stage is free in both CTAs
       }
-      tc::umma_commit(&tmem_full_bar);
+      tc::umma_commit_2sm_mc(&tmem_full_bar, 3);           // both CTAs' epilogues may drain their accumulator rows
     }
   } else {
     const int q = warp & 3;
@@ -128,8 +281,8 @@ conv3x3_tf32_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         }
         if (flags & kRelu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
         if (flags & kMask) {
-          const float4 m = __ldg(msk + j);
-          o.x = m.x > 0.f ? o.x : 0.f; o.y = m.y > 0.f ? o.y : 0.f; o.z = m.z > 0.f ? o.z : 0.f; o.w = m.w > 0.f ? o.w : 0.f;
+          const float4 mm = __ldg(msk + j);
+          o.x = mm.x > 0.f ? o.x : 0.f; o.y = mm.y > 0.f ? o.y : 0.f; o.z = mm.z > 0.f ? o.z : 0.f; o.w = mm.w > 0.f ? o.w : 0.f;
         }
         if (flags & kRound) { o.x = rna_tf32(o.x); o.y = rna_tf32(o.y); o.z = rna_tf32(o.z); o.w = rna_tf32(o.w); }
         dst[j] = o;
@@ -138,7 +291,62 @@ conv3x3_tf32_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 1) tc::tmem_dealloc(tmem_base, BN);
+  tc::cluster_sync_all();                      // the peer's MMAs read this CTA's shared memory until the very end
+  if (warp == 1) tc::tmem_dealloc_2sm(tmem_base, BN);
+}
+
+template <int STAGES>
+static int launch_conv_2cta(const CUtensorMap& mx, const CUtensorMap& mw, const float* bias, const float* msk, float* y,
+                            int H, int W, int Cin, int Cout, int best_log2, int tiles_w, int tiles_h, int total_tiles,
+                            int dil, int flags, cudaStream_t st) {
+  const int smem = STAGES * (kBM + 128) * tc::kTileKBytes + 1024;
+  auto kern = conv3x3_tf32_2cta_kernel<STAGES>;
+  ODW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(total_tiles, Cout / 256);
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ODW_CUDA(cudaLaunchKernelEx(&cfg, kern, mx, mw, bias, msk, y, H, W, Cin, Cout, best_log2, tiles_w, tiles_h, dil, flags));
+  return 0;
+}
+
+// ODWSCL_CONV_CLUSTER=2 turns the 2-CTA weight multicast on, ODWSCL_CONV_MT=1 turns the two-accumulator tiles off
+// (A/B measurements)
+static int conv_env(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && e[0] >= '0' && e[0] <= '9') ? atoi(e) : dflt;
+}
+
+template <int BN, int STAGES, int CL, int MT>
+static int launch_conv_inst(const CUtensorMap& mx, const CUtensorMap& mw, const float* bias, const float* msk, float* y,
+                            int H, int W, int Cin, int Cout, int best_log2, int tiles_w, int tiles_h, int total_tiles,
+                            int dil, int flags, cudaStream_t st) {
+  const int smem = STAGES * (MT * kBM + BN) * tc::kTileKBytes + 1024;
+  auto kern = conv3x3_tf32_kernel<BN, STAGES, CL, MT>;
+  ODW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(odw_cdiv(total_tiles, MT), odw_cdiv(Cout, BN));
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CL > 1 ? 1 : 0;
+  ODW_CUDA(cudaLaunchKernelEx(&cfg, kern, mx, mw, bias, msk, y, H, W, Cin, Cout, best_log2, tiles_w, tiles_h, total_tiles,
+                              dil, flags));
+  return 0;
 }
 
 template <int BN, int STAGES>
@@ -154,6 +362,13 @@ int launch_conv(const float* x, int B, int H, int W, int Cin, const float* wk, c
   }
   const int TW = 1 << best_log2, TH = kBM >> best_log2;
   const int tiles_w = odw_cdiv(W, TW), tiles_h = odw_cdiv(H, TH);
+  const int total_tiles = B * tiles_h * tiles_w;
+  const int n_tiles = odw_cdiv(Cout, BN);
+  // CTA pairs (cta_group::2) for the 256-channel tiles; ODWSCL_CONV_2CTA=0 falls back to one CTA per tile
+  const bool pair = BN == 256 && Cout % 256 == 0 && total_tiles % 2 == 0 && conv_env("ODWSCL_CONV_2CTA", 1) != 0;
+  // two accumulators per CTA (ODWSCL_CONV_MT=2; measured slower at the bench shapes, off by default)
+  const bool mt2 = !pair && BN == 256 && conv_env("ODWSCL_CONV_MT", 1) >= 2 && odw_cdiv(total_tiles, 2) * n_tiles >= ODW_NUM_SMS;
+  const int cl = (pair || (!mt2 && conv_env("ODWSCL_CONV_CLUSTER", 1) >= 2 && total_tiles % 2 == 0)) ? 2 : 1;
   CUtensorMap mx, mw;
   const uint64_t dx[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
   const uint64_t sx[3] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4};
@@ -162,16 +377,23 @@ int launch_conv(const float* x, int B, int H, int W, int Cin, const float* wk, c
   if (rc) return rc;
   const uint64_t dw[2] = {(uint64_t)9 * Cin, (uint64_t)Cout};
   const uint64_t sw[1] = {(uint64_t)9 * Cin * 4};
-  const uint32_t bw[2] = {32, (uint32_t)BN};
+  const uint32_t bw[2] = {32, (uint32_t)(BN / cl)};
   rc = tc::make_tmap_f32(&mw, wk, 2, dw, sw, bw);
   if (rc) return rc;
-  const int smem = STAGES * (kBM + BN) * tc::kTileKBytes + 1024;
-  ODW_CUDA(cudaFuncSetAttribute(conv3x3_tf32_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  dim3 grid(B * tiles_h * tiles_w, odw_cdiv(Cout, BN));
-  conv3x3_tf32_kernel<BN, STAGES><<<grid, 192, smem, st>>>(mx, mw, bias, mask_src ? mask_src : y, y, H, W, Cin, Cout,
-                                                            best_log2, tiles_w, tiles_h, dil, flags);
-  ODW_LAUNCH_CHECK();
-  return 0;
+  const float* msk = mask_src ? mask_src : y;
+  if constexpr (BN == 256) {
+    if (pair)
+      return launch_conv_2cta<6>(mx, mw, bias, msk, y, H, W, Cin, Cout, best_log2, tiles_w, tiles_h, total_tiles, dil,
+                                 flags, st);
+    if (mt2)
+      return launch_conv_inst<BN, 3, 1, 2>(mx, mw, bias, msk, y, H, W, Cin, Cout, best_log2, tiles_w, tiles_h, total_tiles,
+                                           dil, flags, st);
+  }
+  if (cl == 2)
+    return launch_conv_inst<BN, STAGES, 2, 1>(mx, mw, bias, msk, y, H, W, Cin, Cout, best_log2, tiles_w, tiles_h,
+                                              total_tiles, dil, flags, st);
+  return launch_conv_inst<BN, STAGES, 1, 1>(mx, mw, bias, msk, y, H, W, Cin, Cout, best_log2, tiles_w, tiles_h, total_tiles,
+                                            dil, flags, st);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -24,8 +24,9 @@ __device__ __forceinline__ float block_mask_at(const float* __restrict__ cen, in
 }
 
 __global__ void dropblock_sum_kernel(const float* __restrict__ centres, int R, int ph, int pw, int block,
-                                     float* __restrict__ scale_io) {
+                                     float* __restrict__ scale_io, const int32_t* __restrict__ n_valid) {
   const int cells = ph * pw;
+  if (n_valid != nullptr) R = min(R, max(*n_valid, 0));
   float part = 0.f;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < (long long)R * cells;
        t += (long long)gridDim.x * blockDim.x) {
@@ -36,15 +37,22 @@ __global__ void dropblock_sum_kernel(const float* __restrict__ centres, int R, i
   if ((threadIdx.x & 31) == 0 && part != 0.f) atomicAdd(scale_io, part);   // integer-valued: order-free
 }
 
-__global__ void dropblock_scale_kernel(int R, int ph, int pw, float* __restrict__ scale_io) {
+__global__ void dropblock_scale_kernel(int R, int ph, int pw, float* __restrict__ scale_io,
+                                       const int32_t* __restrict__ n_valid) {
+  if (n_valid != nullptr) R = min(R, max(*n_valid, 0));
   scale_io[1] = (float)((long long)R * ph * pw) / scale_io[0];
 }
 
 __global__ void __launch_bounds__(256)
 dropblock_apply_kernel(const float* __restrict__ x, const float* __restrict__ centres, int C, int ph, int pw,
-                       int block, const float* __restrict__ scale_io, float* __restrict__ y) {
+                       int block, const float* __restrict__ scale_io, float* __restrict__ y,
+                       const int32_t* __restrict__ n_valid) {
   extern __shared__ float s_bm[];
   const int r = blockIdx.x, cells = ph * pw;
+  if (n_valid != nullptr && r >= *n_valid) {               // padding row: defined output, no contribution
+    for (int t = threadIdx.x; t < C * cells; t += blockDim.x) y[(size_t)r * C * cells + t] = 0.f;
+    return;
+  }
   const float scale = scale_io[1];
   for (int k = threadIdx.x; k < cells; k += blockDim.x)
     s_bm[k] = block_mask_at(centres + (size_t)r * cells, ph, pw, block, k / pw, k % pw) * scale;
@@ -59,8 +67,9 @@ dropblock_apply_kernel(const float* __restrict__ x, const float* __restrict__ ce
 
 }  // namespace
 
-ODW_API int odwscl_dropblock_f32(const float* x, const float* centres, int R, int C, int ph, int pw, int block,
-                                 float* y, float* scale_io, int reuse_scale, odwscl_stream_t stream) {
+ODW_API int odwscl_dropblock_rows_f32(const float* x, const float* centres, int R, int C, int ph, int pw, int block,
+                                      float* y, float* scale_io, int reuse_scale, const int32_t* n_valid_dev,
+                                      odwscl_stream_t stream) {
   if (R < 0 || C < 0 || ph <= 0 || pw <= 0 || block <= 0) return ODWSCL_EINVAL;
   if (R == 0 || C == 0) return 0;
   if (!x || !centres || !y || !scale_io) return ODWSCL_EINVAL;
@@ -69,12 +78,18 @@ ODW_API int odwscl_dropblock_f32(const float* x, const float* centres, int R, in
     ODW_CUDA(cudaMemsetAsync(scale_io, 0, 2 * sizeof(float), st));
     const long long total = (long long)R * ph * pw;
     dropblock_sum_kernel<<<(int)min((long long)ODW_NUM_SMS, (total + 255) / 256), 256, 0, st>>>(centres, R, ph, pw,
-                                                                                             block, scale_io);
+                                                                                             block, scale_io, n_valid_dev);
     ODW_LAUNCH_CHECK();
-    dropblock_scale_kernel<<<1, 1, 0, st>>>(R, ph, pw, scale_io);
+    dropblock_scale_kernel<<<1, 1, 0, st>>>(R, ph, pw, scale_io, n_valid_dev);
     ODW_LAUNCH_CHECK();
   }
-  dropblock_apply_kernel<<<R, 256, ph * pw * sizeof(float), st>>>(x, centres, C, ph, pw, block, scale_io, y);
+  dropblock_apply_kernel<<<R, 256, ph * pw * sizeof(float), st>>>(x, centres, C, ph, pw, block, scale_io, y,
+                                                                  n_valid_dev);
   ODW_LAUNCH_CHECK();
   return 0;
+}
+
+ODW_API int odwscl_dropblock_f32(const float* x, const float* centres, int R, int C, int ph, int pw, int block,
+                                 float* y, float* scale_io, int reuse_scale, odwscl_stream_t stream) {
+  return odwscl_dropblock_rows_f32(x, centres, R, C, ph, pw, block, y, scale_io, reuse_scale, nullptr, stream);
 }

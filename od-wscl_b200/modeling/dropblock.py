@@ -11,18 +11,18 @@ from .. import capi
 
 class _DropBlockFn(Function):
     @staticmethod
-    def forward(ctx, x, centres, block):
-        y, scale_io = capi.dropblock(x, centres, block)
+    def forward(ctx, x, centres, block, n_valid=None):
+        y, scale_io = capi.dropblock(x, centres, block, n_valid=n_valid)
         ctx.save_for_backward(centres, scale_io)
-        ctx.block = block
+        ctx.block, ctx.n_valid = block, n_valid
         return y
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gy):
         centres, scale_io = ctx.saved_tensors
-        gx, _ = capi.dropblock(gy, centres, ctx.block, scale_io)
-        return gx, None, None
+        gx, _ = capi.dropblock(gy.contiguous(), centres, ctx.block, scale_io, n_valid=ctx.n_valid)
+        return gx, None, None, None
 
 
 class DropBlock2D(nn.Module):
@@ -32,7 +32,8 @@ class DropBlock2D(nn.Module):
         self.block_size = block_size
         self.centre_sampler = None     # test hook: callable(n, h, w, gamma, device) -> float mask
 
-    def forward(self, x):
+    def forward(self, x, n_valid=None):
+        """`n_valid` (int32 device tensor [1], optional): x is a padded batch whose first n_valid rows are real."""
         assert x.dim() == 4, "Expected input with 4 dimensions (bsize, channels, height, width)"
         if not self.training or self.drop_prob == 0.0:
             return x
@@ -44,4 +45,4 @@ class DropBlock2D(nn.Module):
             centres = self.centre_sampler(n, h, w, gamma, x.device)
         else:
             centres = (torch.rand(n, h, w, device=x.device) < gamma).float()   # :42
-        return _DropBlockFn.apply(x.contiguous(), centres.contiguous(), self.block_size)
+        return _DropBlockFn.apply(x.contiguous(), centres.contiguous(), self.block_size, n_valid)

@@ -50,6 +50,17 @@ class RoIRegLossComputation(object):
         self.fg_thresh = cfg.MODEL.ROI_HEADS.FG_IOU_THRESHOLD
         self.batch_aug = True           # False: per-(image,class) drop/noise calls in reference order (RNG replay)
         self.last_state = None          # DiscoveryState of the last call (tests / diagnostics)
+        # Speculative sizing of the augmented-positives batch: K (the number of Phase-A positives) is the ONLY
+        # quantity the step reads back from the device.  With speculative_k the batch is sized from the largest K
+        # seen so far (padded, masked on the device) and no host synchronisation happens inside the step;
+        # `overflow` [1] fp32 is 1.0 when the true K exceeded the bound -- the caller must then discard the step
+        # (bench.py hands it to the fused optimizer as `found_inf`, which skips the update, and redoes the step).
+        self.speculative_k = False
+        self.k_margin = 2.0
+        self.overflow = None
+        self._k_cap = None
+        self._k_host = None
+        self._k_event = None
 
     def __call__(self, class_score, det_score, ref_scores, ref_bbox_preds, sim_feature, clean_pooled_feats,
                  feature_extractor, model_sim, proposals, targets, epsilon=1e-8):
@@ -96,8 +107,45 @@ class RoIRegLossComputation(object):
         scores = (final_score.detach().contiguous(), ref_sm[0].detach().contiguous(), ref_sm[1].detach().contiguous())
         Fm = sim_feature.contiguous()
         st = capi.discover_phase_a(boxes, img_off_d, scores, pair_img_d, pair_cls_d, Ncap, self.p_thres)
+        spec = self.speculative_k and self.batch_aug and P > 0 and self._poll_k_cap() is not None
+        if spec:
+            E, K = self._augmented_positives_speculative(st, P, Ncap, clean_pooled_feats, feature_extractor, model_sim)
+        else:
+            E, K = self._augmented_positives_synced(st, P, clean_pooled_feats, feature_extractor, model_sim)
+        capi.discover_phase_b(st, Fm.detach(), E.detach(), self.nms)
+        Mcap = 3 * K + 3 * sum(sizes[b] for b in pair_img)
+        capi.bank_assemble(st, C - 1, Mcap)
+        self.last_state = st
+        losses["loss_sim"] = self.sim_lmda * supcon_bank_loss(Fm, E, st.row_src, st.row_lab, st.row_w, st.M, Mcap,
+                                                              self.temp)               # loss.py:347
+        return self._refinement_losses(st, losses, accs, final_score, ref_scores, ref_bbox_preds, img_labels_d, sizes,
+                                       offs, pos, same, B, R, C, dev, epsilon)
+
+    # ------------------------------------------------------------------ augmented positives (loss.py:299-310)
+    def _poll_k_cap(self):
+        """Bound for the next speculative step from the K values read back so far (non-blocking)."""
+        if self._k_event is not None and self._k_event.query():
+            k = int(self._k_host[0])
+            cap = (int(k * self.k_margin) + 64 + 63) // 64 * 64
+            self._k_cap = cap if self._k_cap is None else max(self._k_cap, cap)
+            self._k_event = None
+        return self._k_cap
+
+    def _record_k(self, kdev):
+        if self._k_host is None:
+            self._k_host = torch.zeros((1,), dtype=torch.int32).pin_memory()
+        if self._k_event is None:                      # one readback in flight at a time
+            self._k_host.copy_(kdev, non_blocking=True)
+            self._k_event = torch.cuda.Event()
+            self._k_event.record()
+
+    def _augmented_positives_synced(self, st, P, clean_pooled_feats, feature_extractor, model_sim):
         offA_h = st.offA.cpu()                                   # the one host sync of the step
         K = int(offA_h[P]) if P > 0 else 0
+        if self.speculative_k:
+            cap = (int(K * self.k_margin) + 64 + 63) // 64 * 64
+            self._k_cap = cap if self._k_cap is None else max(self._k_cap, cap)
+            self.overflow = torch.zeros((1,), dtype=torch.float32, device=st.offA.device)
         rows = st.rowsA[:K].long()
         if self.batch_aug:
             X = clean_pooled_feats.index_select(0, rows)
@@ -110,13 +158,33 @@ class RoIRegLossComputation(object):
                 noises.append(feature_extractor.noise_pool(Xp))
             aug = torch.cat(drops + noises, dim=0)
         E = model_sim(feature_extractor.forward_neck(aug)).contiguous()                  # [2K,128]
-        capi.discover_phase_b(st, Fm.detach(), E.detach(), self.nms)
-        Mcap = 3 * K + 3 * sum(sizes[b] for b in pair_img)
-        capi.bank_assemble(st, C - 1, Mcap)
-        self.last_state = st
-        losses["loss_sim"] = self.sim_lmda * supcon_bank_loss(Fm, E, st.row_src, st.row_lab, st.row_w, st.M, Mcap,
-                                                              self.temp)               # loss.py:347
+        return E, K
 
+    def _augmented_positives_speculative(self, st, P, Ncap, clean_pooled_feats, feature_extractor, model_sim):
+        """Same arithmetic over a batch padded to the bound Kc: rows past the device-resident K are masked (DropBlock
+        renormalises over the first K rows only), and the [2K,128] layout the discovery kernels address (drop rows,
+        then noise rows, stride K) is rebuilt with a gather -- nothing is read back."""
+        dev = st.offA.device
+        Kc = min(self._k_cap, P * Ncap)
+        kdev = st.offA[P:P + 1]                                   # int32 [1], device
+        k64 = kdev.long()
+        kv = torch.clamp(k64, max=Kc)                             # rows that really exist in the padded batch
+        ar = torch.arange(Kc, device=dev)
+        rows = torch.where(ar < kv, st.rowsA[:Kc].long(), torch.zeros_like(ar))
+        X = clean_pooled_feats.index_select(0, rows)
+        aug = torch.cat([feature_extractor.drop_pool(X, n_valid=kdev), feature_extractor.noise_pool(X)], dim=0)
+        Epad = model_sim(feature_extractor.forward_neck(aug))     # [2Kc,128]
+        j = torch.arange(2 * P * Ncap, device=dev)                # K <= P*Ncap always: every address the kernels form is in range
+        jj = j - k64
+        idx = torch.where(j < k64, torch.where(j < kv, j, torch.zeros_like(j)),
+                          torch.where((jj < kv) & (j < 2 * k64), jj + Kc, torch.zeros_like(j)))
+        E = Epad.index_select(0, idx).contiguous()
+        self.overflow = (k64 > Kc).float()
+        self._record_k(kdev)
+        return E, Kc
+
+    def _refinement_losses(self, st, losses, accs, final_score, ref_scores, ref_bbox_preds, img_labels_d, sizes, offs,
+                           pos, same, B, R, C, dev, epsilon):
         # ---- pseudo labels for the three refinement branches (loss.py:364-368 -> od_layer)
         pl, lw, rt = capi.od_layer(st, self.fg_thresh)
 

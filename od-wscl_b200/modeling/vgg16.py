@@ -110,8 +110,8 @@ class VGG16FC67ROIFeatureExtractor(nn.Module):
     def forward_dropblock(self, pooled_feats, proposals):  # vgg16.py:165-167
         return self.dropblock(pooled_feats)
 
-    def drop_pool(self, pooled_feats):                   # vgg16.py:173-175
-        return self.sim_drop(pooled_feats)
+    def drop_pool(self, pooled_feats, n_valid=None):     # vgg16.py:173-175
+        return self.sim_drop(pooled_feats, n_valid) if n_valid is not None else self.sim_drop(pooled_feats)
 
     def noise_pool(self, pooled_feats):                  # vgg16.py:177-180
         if self.noise_sampler is not None:

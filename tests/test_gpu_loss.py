@@ -240,3 +240,57 @@ def test_model_cfg1_golden(golden):
     sum(losses.values()).backward()
     gsum = sum(float(p.grad.abs().sum()) for p in model.parameters() if p.grad is not None)
     assert np.isfinite(gsum) and gsum > 0
+
+
+def test_speculative_k_matches_synced():
+    """The step without a host sync (augmented-positives batch padded to a bound on K, masked on the device) computes
+    the same losses and gradients as the path that reads K back; an exceeded bound raises `overflow` instead."""
+    from odwscl_b200.config import cfg
+    from odwscl_b200.modeling import build_detection_model
+    from odwscl_b200.structures import BoxList
+    model = build_detection_model(cfg)
+    model.load_state_dict(orc.synth_state_dict(21, seed=0), strict=True)
+    model.cuda().train()
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    images, boxes, labels = orc.synth_batch(2, 200, 400, 320, 21, seed=77)
+    props = [BoxList(b.cuda(), (400, 320), "xyxy") for b in boxes]
+    targets = []
+    for lab in labels:
+        t = BoxList(torch.zeros((len(lab), 4)), (400, 320), "xyxy")
+        t.add_field("labels", torch.as_tensor(lab))
+        targets.append(t)
+    fe, ev = model.roi_heads.feature_extractor, model.roi_heads.loss_evaluator
+
+    def run():
+        g = torch.Generator().manual_seed(99)      # CPU generator: rand(n)[:k] == rand(k), so padded batches see the same masks
+        sampler = lambda n, h, w, gamma, dev: (torch.rand(n, h, w, generator=g) < gamma).float().to(dev)
+        fe.dropblock.centre_sampler = sampler
+        fe.sim_drop.centre_sampler = sampler
+        gn = torch.Generator().manual_seed(7)
+        fe.noise_sampler = lambda shape, dev: torch.randn(tuple(shape), generator=gn).to(dev)
+        model.zero_grad(set_to_none=True)
+        losses, _ = model(images.cuda(), targets, props)
+        sum(losses.values()).backward()
+        grads = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+        return {k: float(v) for k, v in losses.items()}, grads
+
+    ev.speculative_k = False
+    ref_l, ref_g = run()
+    K = int(ev.last_state.offA[-1])
+    assert K > 0
+    ev.speculative_k = True
+    run()                                          # first call: reads K back once and sets the bound
+    assert ev._k_cap is not None and ev._k_cap >= K
+    got_l, got_g = run()                           # no host sync in here
+    assert float(ev.overflow) == 0.0
+    for k in ref_l:
+        assert abs(got_l[k] - ref_l[k]) <= 1e-5 * max(abs(ref_l[k]), 1e-3), (k, got_l[k], ref_l[k])
+    for k in ref_g:      # scatter-add / split-K reductions use fp32 atomics: run-to-run order noise, scaled by the tensor
+        torch.testing.assert_close(got_g[k], ref_g[k], rtol=2e-4, atol=2e-4 * float(ref_g[k].abs().max()) + 1e-9)
+    ev._k_cap = 1                                  # bound too small: flagged, finite, nothing out of range
+    ev._k_event = None
+    bad_l, _ = run()
+    assert float(ev.overflow) == 1.0
+    assert all(np.isfinite(v) for v in bad_l.values())
