@@ -65,7 +65,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.monotonic(), [x.strip() for x in line.split(",")]))
+
+    def window(self, t0, t1):
+        """Keep only the samples taken inside [t0, t1] (the timed regions)."""
+        self.t0, self.t1 = t0, t1
 
     def stop(self):
         if self.proc is None:
@@ -75,10 +79,12 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             pass
-        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
-        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        t0, t1 = getattr(self, "t0", None), getattr(self, "t1", None)
+        rows = [r for t, r in self.rows if t0 is None or (t0 <= t <= t1 + 0.15)]
+        sm = sorted(int(float(r[0])) for r in rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        reasons = sorted({n for r in rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
 
@@ -233,12 +239,15 @@ def run_ours(args):
         loss_h.copy_(total.detach().view(1), non_blocking=True)
         torch.cuda.current_stream().synchronize()          # the user reads the loss every step
 
+    # nvidia-smi is started BEFORE the warm-up: its NVML initialisation briefly stalls kernel launches, which must not
+    # land inside the timed region; only the samples taken inside the timed regions are kept.
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         resident_step()
     torch.cuda.synchronize()
     overflowed()
-    sampler = ClockSampler(local)
-    sampler.start()
+    t_timed0 = time.monotonic()
     l0 = capi.launch_count
     if args.profile_range:
         torch.cuda.synchronize()
@@ -257,6 +266,7 @@ def run_ours(args):
         e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
     skipped_e2e = overflowed()
+    sampler.window(t_timed0, time.monotonic())
     clocks = sampler.stop()
     props_per_step = sharding.proposals_per_step(world, B_PER_GPU, N_PROP)
     value = props_per_step * args.steps / (ms / 1e3)

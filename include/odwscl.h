@@ -59,6 +59,12 @@ int odwscl_roi_pool_fwd_nhwc_f32(const float* feat_nhwc, int B, int C, int H, in
                                  float scale, float* out, int32_t* argmax, odwscl_stream_t stream);
 int odwscl_roi_pool_bwd_nhwc_f32(const float* grad_out, const int32_t* argmax, const float* rois, int R, int B,
                                  int C, int H, int W, float* grad_in_nhwc, odwscl_stream_t stream);
+/* A4 for a pooled tensor with several consumers (weak_head.py:107-120): up to two dense gradients [R,C,7,7] and
+ * one sparse one (srows [S] int64 roi indices, sgrad [S,C,7,7]) are summed while they are scattered.  EINVAL when
+ * H*W*4 B exceeds the shared-memory plane (caller sums and uses odwscl_roi_pool_bwd_nhwc_f32). */
+int odwscl_roi_pool_bwd_nhwc_multi_f32(const float* grad_out, const float* grad_out2, const int64_t* srows,
+                                       const float* sgrad, int S, const int32_t* argmax, const float* rois, int R,
+                                       int B, int C, int H, int W, float* grad_in_nhwc, odwscl_stream_t stream);
 
 /* ---- A5: ROIAlign (legacy, non-aligned).  Replaces _C.roi_align_forward/backward
  * (csrc/ROIAlign.h:11-45 -> csrc/cuda/ROIAlign_cuda.cu:64-122,177-254). */

@@ -21,7 +21,7 @@ launch_count = 0          # kernels-launching C-ABI calls made so far (bench.py 
 # kernels enqueued per entry point (for the `gpu_launches` bench key)
 _LAUNCHES = {
     "odwscl_roi_pool_fwd_f32": 2, "odwscl_roi_pool_bwd_f32": 1, "odwscl_roi_pool_fwd_nhwc_f32": 1,
-    "odwscl_roi_pool_bwd_nhwc_f32": 1, "odwscl_roi_align_fwd_f32": 1,
+    "odwscl_roi_pool_bwd_nhwc_f32": 1, "odwscl_roi_pool_bwd_nhwc_multi_f32": 1, "odwscl_roi_align_fwd_f32": 1,
     "odwscl_roi_align_bwd_f32": 1, "odwscl_box_iou_f32": 1, "odwscl_nms_f32": 1, "odwscl_nms_legacy_f32": 1,
     "odwscl_discover_phase_a_f32": 2, "odwscl_discover_phase_b_f32": 2, "odwscl_bank_assemble": 1,
     "odwscl_supcon_fwd_f32": 2, "odwscl_supcon_bwd_f32": 1, "odwscl_od_layer_f32": 1,
@@ -37,6 +37,7 @@ _SIGS = {
     "odwscl_roi_pool_bwd_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "odwscl_roi_pool_fwd_nhwc_f32": (_I, [_P, _I, _I, _I, _I, _P, _I, _F, _P, _P, _P]),
     "odwscl_roi_pool_bwd_nhwc_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "odwscl_roi_pool_bwd_nhwc_multi_f32": (_I, [_P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "odwscl_roi_align_fwd_f32": (_I, [_P, _I, _I, _I, _I, _P, _I, _F, _I, _I, _I, _P, _P]),
     "odwscl_roi_align_bwd_f32": (_I, [_P, _P, _I, _F, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "odwscl_box_iou_f32": (_I, [_P, _I, _P, _I, _I, _P, _P]),
@@ -106,6 +107,9 @@ _WORK = {
     # (grad, argmax, rois, R, B, C, H, W, ...): grad_out + argmax reads, zero + write of the map
     "odwscl_roi_pool_bwd_nhwc_f32": lambda a: ("byte", 8.0 * a[3] * a[5] * 49 + 8.0 * a[4] * a[5] * a[6] * a[7]),
     "odwscl_roi_pool_bwd_f32": lambda a: ("byte", 8.0 * a[3] * a[5] * a[8] * a[9] + 8.0 * a[4] * a[5] * a[6] * a[7]),
+    # (g1, g2, srows, sgrad, S, argmax, rois, R, B, C, H, W, ...): same algorithmic figure as the single-source call
+    # (SURVEY 8d counts ONE gradient read; the second dense source replaces a separate accumulate pass)
+    "odwscl_roi_pool_bwd_nhwc_multi_f32": lambda a: ("byte", 8.0 * a[7] * a[9] * 49 + 8.0 * a[8] * a[9] * a[10] * a[11]),
     # (F, N, out, ...): N x N x 128 contraction
     "odwscl_sim_nxn_f32": lambda a: ("flop", 2.0 * a[1] * a[1] * 128),
     # (A, B, C, M, N, K, ...)
@@ -154,14 +158,17 @@ def _is_nhwc(t):
     return t.dim() == 4 and t.shape[1] > 1 and not t.is_contiguous() and t.is_contiguous(memory_format=torch.channels_last)
 
 
-def roi_pool_forward(feat, rois, scale, ph, pw):
+def roi_pool_forward(feat, rois, scale, ph, pw, out=None):
+    """`out` (optional): a contiguous [R,C,ph,pw] fp32 buffer to pool into (e.g. the first half of a larger batch)."""
     rois = _chk(rois, torch.float32, "rois")
     B, C, H, W = feat.shape
     R = rois.shape[0]
     nhwc = _is_nhwc(feat) and ph == 7 and pw == 7 and C % 4 == 0 and feat.dtype == torch.float32 and feat.is_cuda
     if not nhwc:
         feat = _chk(feat, torch.float32, "input")
-    out = torch.empty((R, C, ph, pw), dtype=torch.float32, device=feat.device)
+    if out is None:
+        out = torch.empty((R, C, ph, pw), dtype=torch.float32, device=feat.device)
+    assert out.shape == (R, C, ph, pw) and out.is_contiguous() and out.dtype == torch.float32
     arg = torch.empty((R, C, ph, pw), dtype=torch.int32, device=feat.device)
     if out.numel() == 0:
         return out, arg
@@ -190,6 +197,28 @@ def roi_pool_backward(grad, rois, argmax, ph, pw, B, C, H, W, channels_last=Fals
         _call("odwscl_roi_pool_bwd_f32", _ptr(grad), _ptr(argmax), _ptr(rois), rois.shape[0], B, C, H, W, ph, pw,
               _ptr(gin), _stream())
     return gin
+
+
+def roi_pool_backward_multi(grad, grad2, srows, sgrad, rois, argmax, B, C, H, W):
+    """NHWC grad map of a pooled tensor with up to two dense consumers and one sparse (gathered-rows) consumer.
+    Returns None when the map does not fit the plane-centric kernel (the caller sums the gradients itself)."""
+    if H * W * 4 > 220 * 1024:
+        return None
+    grad, rois = _chk(grad, torch.float32, "grad"), _chk(rois, torch.float32, "rois")
+    argmax = _chk(argmax, torch.int32, "argmax")
+    if grad2 is not None:
+        grad2 = _chk(grad2, torch.float32, "grad2")
+        assert grad2.shape == grad.shape
+    S = 0
+    if srows is not None and srows.numel() > 0:
+        srows, sgrad = _chk(srows, torch.int64, "srows"), _chk(sgrad, torch.float32, "sgrad")
+        S = srows.numel()
+        assert sgrad.shape[0] == S and sgrad.numel() == S * C * 49
+    gin = torch.empty((B, H, W, C), dtype=torch.float32, device=grad.device)
+    with torch.cuda.device(grad.device):
+        _call("odwscl_roi_pool_bwd_nhwc_multi_f32", _ptr(grad), _ptr(grad2), _ptr(srows) if S else None,
+              _ptr(sgrad) if S else None, S, _ptr(argmax), _ptr(rois), rois.shape[0], B, C, H, W, _ptr(gin), _stream())
+    return gin.permute(0, 3, 1, 2)
 
 
 def roi_align_forward(feat, rois, scale, ph, pw, sampling_ratio):
@@ -266,12 +295,13 @@ def gemm_nt_tf32(A, B):
     return C
 
 
-def dropblock(x, centres, block, scale_io=None, n_valid=None):
+def dropblock(x, centres, block, scale_io=None, n_valid=None, out=None):
     """y = x * block_mask * numel/sum.  Pass the returned scale_io back in for the backward.  `n_valid` (int32 device
     tensor [1]) restricts the renormalisation and the output to the first n_valid rows of a padded batch."""
     x, centres = _chk(x, torch.float32, "x"), _chk(centres, torch.float32, "centres")
     R, C, ph, pw = x.shape
-    y = torch.empty_like(x)
+    y = torch.empty_like(x) if out is None else out
+    assert y.shape == x.shape and y.is_contiguous() and y.dtype == torch.float32
     reuse = scale_io is not None
     if scale_io is None:
         scale_io = torch.empty((2,), dtype=torch.float32, device=x.device)

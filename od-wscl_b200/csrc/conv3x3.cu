@@ -552,52 +552,66 @@ __global__ void bias_grad_kernel(const float* __restrict__ dz, long long P, int 
 }
 
 // ---------------------------------------------------------------------------------------------
-// conv1_1: Cin = 3.  thread = (pixel, 16-channel group); 4 adjacent lanes write one pixel's 64 channels.
+// conv1_1: Cin = 3 (K = 27: not tensor-core shaped).  CTA = 128 consecutive pixels of one image row; the 3 x 3-row
+// input patch and the 27 x 64 weights sit in shared memory; thread = (pixel pair, 32-channel half), so one broadcast
+// 16-byte weight load feeds 8 FFMA (64 accumulators per thread).  Reads the NCHW image, writes NHWC.
+constexpr int kC3Tile = 128;
 template <int COUT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 conv3x3_c3_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                   float* __restrict__ y, int B, int H, int W, int relu) {
-  constexpr int G = COUT / 16;
-  __shared__ float sw[27 * COUT];     // [tap*3+ci][co]
-  __shared__ float sb[COUT];
+  static_assert(COUT == 64, "two 32-channel halves");
+  __shared__ __align__(16) float sw[27 * COUT];     // [tap*3+ci][co]
+  __shared__ __align__(16) float sb[COUT];
+  __shared__ float sx[3][3][kC3Tile + 4];           // [ci][row][col + 1], zero outside the image
+  const int tiles_w = (W + kC3Tile - 1) / kC3Tile;
+  int t = blockIdx.x;
+  const int w0 = (t % tiles_w) * kC3Tile; t /= tiles_w;
+  const int hq = t % H;
+  const int bq = t / H;
   for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) {
     const int co = i % COUT, k = i / COUT;          // k = (r*3+s)*3 + ci ; torch layout [co][ci][r][s]
     const int ci = k % 3, tap = k / 3;
     sw[i] = w[(co * 3 + ci) * 9 + tap];
   }
   for (int i = threadIdx.x; i < COUT; i += blockDim.x) sb[i] = bias ? bias[i] : 0.f;
+  const float* xb = x + (size_t)bq * 3 * H * W;
+  for (int i = threadIdx.x; i < 9 * (kC3Tile + 2); i += blockDim.x) {
+    const int col = i % (kC3Tile + 2), rc = i / (kC3Tile + 2);
+    const int r = rc % 3, ci = rc / 3;
+    const int hh = hq + r - 1, ww = w0 + col - 1;
+    sx[ci][r][col] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(xb + ((size_t)ci * H + hh) * W + ww) : 0.f;
+  }
   __syncthreads();
-  const long long total = (long long)B * H * W * G;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(idx % G);
-    const long long pix = idx / G;
-    const int wq = (int)(pix % W);
-    const int hq = (int)((pix / W) % H);
-    const int bq = (int)(pix / ((long long)W * H));
-    float acc[16];
+  const int pp = threadIdx.x & 63, half = threadIdx.x >> 6;
+  float a0[32], a1[32];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = sb[g * 16 + j];
-    const float* xb = x + (size_t)bq * 3 * H * W;
+  for (int j = 0; j < 32; ++j) a0[j] = a1[j] = sb[half * 32 + j];
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const int hh = hq + r - 1;
-      if (hh < 0 || hh >= H) continue;
+  for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const int ww = wq + s - 1;
-        if (ww < 0 || ww >= W) continue;
+    for (int q = 0; q < 3; ++q)
 #pragma unroll
-        for (int ci = 0; ci < 3; ++ci) {
-          const float xv = __ldg(xb + ((size_t)ci * H + hh) * W + ww);
-          const float* wr = sw + ((r * 3 + s) * 3 + ci) * COUT + g * 16;
+      for (int ci = 0; ci < 3; ++ci) {
+        const float x0 = sx[ci][r][2 * pp + q], x1 = sx[ci][r][2 * pp + 1 + q];
+        const float4* wr = reinterpret_cast<const float4*>(sw + ((r * 3 + q) * 3 + ci) * COUT + half * 32);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) acc[j] = fmaf(xv, wr[j], acc[j]);
+        for (int j = 0; j < 8; ++j) {
+          const float4 wv = wr[j];
+          a0[4 * j] = fmaf(x0, wv.x, a0[4 * j]);         a1[4 * j] = fmaf(x1, wv.x, a1[4 * j]);
+          a0[4 * j + 1] = fmaf(x0, wv.y, a0[4 * j + 1]); a1[4 * j + 1] = fmaf(x1, wv.y, a1[4 * j + 1]);
+          a0[4 * j + 2] = fmaf(x0, wv.z, a0[4 * j + 2]); a1[4 * j + 2] = fmaf(x1, wv.z, a1[4 * j + 2]);
+          a0[4 * j + 3] = fmaf(x0, wv.w, a0[4 * j + 3]); a1[4 * j + 3] = fmaf(x1, wv.w, a1[4 * j + 3]);
         }
       }
-    }
-    float4* dst = reinterpret_cast<float4*>(y + (size_t)pix * COUT + g * 16);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+  for (int e = 0; e < 2; ++e) {
+    const int wq = w0 + 2 * pp + e;
+    if (wq >= W) continue;
+    const float* acc = e ? a1 : a0;
+    float4* dst = reinterpret_cast<float4*>(y + (((size_t)bq * H + hq) * W + wq) * COUT + half * 32);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
       float4 o = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
       if (relu & kRelu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
       if (relu & kRound) { o.x = rna_tf32(o.x); o.y = rna_tf32(o.y); o.z = rna_tf32(o.z); o.w = rna_tf32(o.w); }
@@ -706,9 +720,9 @@ ODW_API int odwscl_conv3x3_c3_f32(const float* x_nchw, int B, int H, int W, cons
   if (B < 0 || H < 0 || W < 0 || Cout != 64) return ODWSCL_EINVAL;
   if ((long long)B * H * W == 0) return 0;
   if (!x_nchw || !w_oihw || !y_nhwc) return ODWSCL_EINVAL;
-  const long long total = (long long)B * H * W * 4;
-  const int blocks = (int)min((long long)ODW_NUM_SMS * 8, (total + 255) / 256);
-  conv3x3_c3_kernel<64><<<blocks, 256, 0, (cudaStream_t)stream>>>(x_nchw, w_oihw, bias, y_nhwc, B, H, W, relu);
+  const long long blocks = (long long)B * H * odw_cdiv(W, kC3Tile);
+  if (blocks > 0x7fffffffLL) return ODWSCL_EINVAL;
+  conv3x3_c3_kernel<64><<<(int)blocks, 128, 0, (cudaStream_t)stream>>>(x_nchw, w_oihw, bias, y_nhwc, B, H, W, relu);
   ODW_LAUNCH_CHECK();
   return 0;
 }

@@ -215,8 +215,10 @@ constexpr int kBwdChunkRois = 512;
 
 template <int NCH, bool NHWC>
 __global__ void __launch_bounds__(kBwdThreads, 1)
-roi_pool_bwd_plane_kernel(const float* __restrict__ grad_out, const int32_t* __restrict__ argmax,
-                          const float* __restrict__ rois, int R, int C, int HW, float* __restrict__ grad_in) {
+roi_pool_bwd_plane_kernel(const float* __restrict__ grad_out, const float* __restrict__ grad_out2,
+                          const int64_t* __restrict__ srows, const float* __restrict__ sgrad, int S,
+                          const int32_t* __restrict__ argmax, const float* __restrict__ rois, int R, int C, int HW,
+                          float* __restrict__ grad_in) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* acc = reinterpret_cast<float*>(smem_raw);                         // [HW][NCH]
   __shared__ int s_list[kBwdChunkRois];
@@ -244,8 +246,26 @@ roi_pool_bwd_plane_kernel(const float* __restrict__ grad_out, const int32_t* __r
     for (int it = threadIdx.x; it < items; it += blockDim.x) {
       const int rl = it / kVec, q = it - rl * kVec;
       const size_t off = ((size_t)s_list[rl] * C + (size_t)cg * NCH) * 49 + 4 * q;
-      const float4 g = __ldcs(reinterpret_cast<const float4*>(grad_out + off));
+      float4 g = __ldcs(reinterpret_cast<const float4*>(grad_out + off));
+      if (grad_out2 != nullptr) {                  // second consumer of the pooled features: summed on the fly
+        const float4 g2 = __ldcs(reinterpret_cast<const float4*>(grad_out2 + off));
+        g.x += g2.x; g.y += g2.y; g.z += g2.z; g.w += g2.w;
+      }
       const int4 a = __ldcs(reinterpret_cast<const int4*>(argmax + off));
+      const int e = 4 * q;
+      if (a.x >= 0) atomicAdd(acc + a.x * NCH + (e) / 49, g.x);
+      if (a.y >= 0) atomicAdd(acc + a.y * NCH + (e + 1) / 49, g.y);
+      if (a.z >= 0) atomicAdd(acc + a.z * NCH + (e + 2) / 49, g.z);
+      if (a.w >= 0) atomicAdd(acc + a.w * NCH + (e + 3) / 49, g.w);
+    }
+    // sparse consumer: gradients of a few gathered rows (the contrastive branch's augmented positives)
+    const int sitems = S * kVec;
+    for (int it = threadIdx.x; it < sitems; it += blockDim.x) {
+      const int k = it / kVec, q = it - k * kVec;
+      const long long r = srows[k];
+      if (r < r0 || r >= r1 || (int)__ldg(rois + (size_t)r * 5) != b) continue;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(sgrad + ((size_t)k * C + (size_t)cg * NCH) * 49 + 4 * q));
+      const int4 a = __ldg(reinterpret_cast<const int4*>(argmax + ((size_t)r * C + (size_t)cg * NCH) * 49 + 4 * q));
       const int e = 4 * q;
       if (a.x >= 0) atomicAdd(acc + a.x * NCH + (e) / 49, g.x);
       if (a.y >= 0) atomicAdd(acc + a.y * NCH + (e + 1) / 49, g.y);
@@ -258,7 +278,14 @@ roi_pool_bwd_plane_kernel(const float* __restrict__ grad_out, const int32_t* __r
       const int rl = it / kRun, e = it - rl * kRun;
       const size_t off = ((size_t)s_list[rl] * C + (size_t)cg * NCH) * 49 + e;
       const int a = __ldcs(argmax + off);
-      if (a >= 0) atomicAdd(acc + a * NCH + e / 49, __ldcs(grad_out + off));
+      if (a >= 0) atomicAdd(acc + a * NCH + e / 49, __ldcs(grad_out + off) + (grad_out2 ? __ldcs(grad_out2 + off) : 0.f));
+    }
+    for (int it = threadIdx.x; it < S * kRun; it += blockDim.x) {
+      const int k = it / kRun, e = it - k * kRun;
+      const long long r = srows[k];
+      if (r < r0 || r >= r1 || (int)__ldg(rois + (size_t)r * 5) != b) continue;
+      const int a = __ldg(argmax + ((size_t)r * C + (size_t)cg * NCH) * 49 + e);
+      if (a >= 0) atomicAdd(acc + a * NCH + e / 49, __ldg(sgrad + ((size_t)k * C + (size_t)cg * NCH) * 49 + e));
     }
   }
   __syncthreads();
@@ -284,13 +311,21 @@ roi_pool_bwd_plane_kernel(const float* __restrict__ grad_out, const int32_t* __r
   }
 }
 
+struct BwdExtra {                 // optional extra consumers of the pooled features (all device pointers)
+  const float* grad_out2;
+  const int64_t* srows;
+  const float* sgrad;
+  int S;
+};
+
 template <int NCH, bool NHWC>
 static int launch_bwd_plane(const float* grad_out, const int32_t* argmax, const float* rois, int R, int B, int C,
-                            int HW, float* grad_in, cudaStream_t st) {
+                            int HW, float* grad_in, cudaStream_t st, BwdExtra ex) {
   const int smem = HW * NCH * (int)sizeof(float);
   ODW_CUDA(cudaFuncSetAttribute(roi_pool_bwd_plane_kernel<NCH, NHWC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   dim3 grid(C / NCH, B, odw_cdiv(R, kBwdChunkRois));
-  roi_pool_bwd_plane_kernel<NCH, NHWC><<<grid, kBwdThreads, smem, st>>>(grad_out, argmax, rois, R, C, HW, grad_in);
+  roi_pool_bwd_plane_kernel<NCH, NHWC><<<grid, kBwdThreads, smem, st>>>(grad_out, ex.grad_out2, ex.srows, ex.sgrad, ex.S,
+                                                                         argmax, rois, R, C, HW, grad_in);
   ODW_LAUNCH_CHECK();
   return 0;
 }
@@ -298,12 +333,12 @@ static int launch_bwd_plane(const float* grad_out, const int32_t* argmax, const 
 // picks the widest channel group whose plane fits in shared memory; false = no plane-centric path (7x7 only)
 template <bool NHWC>
 static int bwd_plane_dispatch(const float* grad_out, const int32_t* argmax, const float* rois, int R, int B, int C,
-                              int HW, float* grad_in, cudaStream_t st, bool* done) {
+                              int HW, float* grad_in, cudaStream_t st, bool* done, BwdExtra ex = BwdExtra{nullptr, nullptr, nullptr, 0}) {
   const size_t kMaxSmem = 220 * 1024;
   *done = true;
-  if (C % 4 == 0 && (size_t)HW * 16 <= kMaxSmem) return launch_bwd_plane<4, NHWC>(grad_out, argmax, rois, R, B, C, HW, grad_in, st);
-  if (C % 2 == 0 && (size_t)HW * 8 <= kMaxSmem) return launch_bwd_plane<2, NHWC>(grad_out, argmax, rois, R, B, C, HW, grad_in, st);
-  if ((size_t)HW * 4 <= kMaxSmem) return launch_bwd_plane<1, NHWC>(grad_out, argmax, rois, R, B, C, HW, grad_in, st);
+  if (C % 4 == 0 && (size_t)HW * 16 <= kMaxSmem) return launch_bwd_plane<4, NHWC>(grad_out, argmax, rois, R, B, C, HW, grad_in, st, ex);
+  if (C % 2 == 0 && (size_t)HW * 8 <= kMaxSmem) return launch_bwd_plane<2, NHWC>(grad_out, argmax, rois, R, B, C, HW, grad_in, st, ex);
+  if ((size_t)HW * 4 <= kMaxSmem) return launch_bwd_plane<1, NHWC>(grad_out, argmax, rois, R, B, C, HW, grad_in, st, ex);
   *done = false;
   return 0;
 }
@@ -394,4 +429,26 @@ ODW_API int odwscl_roi_pool_bwd_nhwc_f32(const float* grad_out, const int32_t* a
   roi_pool_bwd_kernel<<<blocks, 256, 0, st>>>(grad_out, argmax, rois, total, C, H * W, 49, grad_in_nhwc, 1);
   ODW_LAUNCH_CHECK();
   return 0;
+}
+
+// Backward of a pooled-feature tensor with several consumers (weak_head.py:107-120: fc6 on the clean features, DropBlock
+// -> fc6 on the augmented ones, and the contrastive branch's gathered rows): the gradients are summed while they are
+// scattered, instead of being materialised as one more [R,C,7,7] tensor per consumer.  grad_out2, and the sparse
+// (srows [S] int64, sgrad [S,C,7,7]) source, may be null / empty.  Returns ODWSCL_EINVAL when the map does not fit the
+// plane-centric kernel (the caller then sums the gradients itself and calls odwscl_roi_pool_bwd_nhwc_f32).
+ODW_API int odwscl_roi_pool_bwd_nhwc_multi_f32(const float* grad_out, const float* grad_out2, const int64_t* srows,
+                                               const float* sgrad, int S, const int32_t* argmax, const float* rois, int R,
+                                               int B, int C, int H, int W, float* grad_in_nhwc, odwscl_stream_t stream) {
+  if (B < 0 || C < 0 || H < 0 || W < 0 || R < 0 || S < 0) return ODWSCL_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t bytes = (size_t)B * C * H * W * sizeof(float);
+  if (bytes == 0) return 0;
+  if (!grad_in_nhwc) return ODWSCL_EINVAL;
+  if ((size_t)H * W * 4 > 220 * 1024) return ODWSCL_EINVAL;
+  ODW_CUDA(cudaMemsetAsync(grad_in_nhwc, 0, bytes, st));
+  if (R == 0) return 0;
+  if (!grad_out || !argmax || !rois || (S > 0 && (!srows || !sgrad))) return ODWSCL_EINVAL;
+  bool done = false;
+  return bwd_plane_dispatch<true>(grad_out, argmax, rois, R, B, C, H * W, grad_in_nhwc, st, &done,
+                                  BwdExtra{grad_out2, srows, sgrad, S});
 }

@@ -38,6 +38,96 @@ class _ROIPool(Function):
 roi_pool = _ROIPool.apply
 
 
+class _PoolAugFn(Function):
+    """ROIPool + DropBlock of the pooled features into ONE [2R,C,7,7] buffer (rows [0,R) clean, [R,2R) augmented), so
+    fc6/fc7 run once over both (weak_head.py:107-113: weights read once, one WGRAD, no gradient accumulation pass) and
+    the backward scatters every consumer's gradient in one ROIPool-backward launch: the clean half, the DropBlock
+    backward of the augmented half, and the rows the contrastive branch gathered (stashed by _GatherRowsFn)."""
+
+    @staticmethod
+    def forward(ctx, input, roi, output_size, spatial_scale, centres, block, stash):
+        ph, pw = _pair(output_size)
+        R, C = roi.shape[0], input.shape[1]
+        buf = torch.empty((2 * R, C, ph, pw), dtype=torch.float32, device=input.device)
+        _, argmax = capi.roi_pool_forward(input, roi, spatial_scale, ph, pw, out=buf[:R])
+        _, scale_io = capi.dropblock(buf[:R], centres, block, out=buf[R:])
+        ctx.save_for_backward(roi, argmax, centres, scale_io)
+        ctx.block, ctx.stash, ctx.input_shape, ctx.R = block, stash, input.size(), R
+        ctx.channels_last = capi._is_nhwc(input)
+        ctx.out_hw = (ph, pw)
+        return buf
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        rois, argmax, centres, scale_io = ctx.saved_tensors
+        R = ctx.R
+        bs, ch, h, w = ctx.input_shape
+        g = g.contiguous()
+        g_aug, _ = capi.dropblock(g[R:], centres, ctx.block, scale_io)            # DropBlock backward of the augmented half
+        srows, sgrad = ctx.stash.pop("rows", None), ctx.stash.pop("grads", None)
+        gin = capi.roi_pool_backward_multi(g[:R], g_aug, srows, sgrad, rois, argmax, bs, ch, h, w) \
+            if ctx.channels_last and ctx.out_hw == (7, 7) else None
+        if gin is None:                                                          # maps too large for the plane kernel
+            tot = g[:R] + g_aug
+            if srows is not None and srows.numel() > 0:
+                tot.index_add_(0, srows, sgrad)
+            gin = capi.roi_pool_backward(tot, rois, argmax, ctx.out_hw[0], ctx.out_hw[1], bs, ch, h, w,
+                                         channels_last=ctx.channels_last)
+        return gin, None, None, None, None, None, None
+
+
+class _GatherRowsFn(Function):
+    """rows of the clean half of a _PoolAugFn buffer; the gradient is handed to that node through `stash` instead of
+    being expanded to a dense zero-filled [R,C,7,7] tensor (the graph edge to `buf` keeps the execution order)."""
+
+    @staticmethod
+    def forward(ctx, buf, rows, R, stash):
+        ctx.stash = stash
+        ctx.save_for_backward(rows)
+        return buf[:R].index_select(0, rows)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (rows,) = ctx.saved_tensors
+        if "rows" in ctx.stash:                                                  # a second gather of the same step
+            ctx.stash["rows"] = torch.cat([ctx.stash["rows"], rows])
+            ctx.stash["grads"] = torch.cat([ctx.stash["grads"], g.contiguous()])
+        else:
+            ctx.stash["rows"], ctx.stash["grads"] = rows, g.contiguous()
+        return None, None, None, None
+
+
+class _SplitRowsFn(Function):
+    """x[:R], x[R:] as two outputs whose backward is ONE concatenation (instead of two zero-padded slices + an add)."""
+
+    @staticmethod
+    def forward(ctx, x, R):
+        ctx.R, ctx.shape = R, x.shape
+        return x[:R], x[R:]
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g1, g2):
+        out = torch.empty(ctx.shape, dtype=g1.dtype if g1 is not None else g2.dtype,
+                          device=g1.device if g1 is not None else g2.device)
+        if g1 is None:
+            out[:ctx.R].zero_()
+        else:
+            out[:ctx.R].copy_(g1)
+        if g2 is None:
+            out[ctx.R:].zero_()
+        else:
+            out[ctx.R:].copy_(g2)
+        return out, None
+
+
+pool_and_augment = _PoolAugFn.apply
+gather_rows = _GatherRowsFn.apply
+split_rows = _SplitRowsFn.apply
+
+
 class ROIPool(nn.Module):
     def __init__(self, output_size, spatial_scale):
         super().__init__()

@@ -19,6 +19,8 @@ from torch.autograd.function import once_differentiable
 
 from .. import capi
 
+OVERLAP_WGRAD = True       # run each layer's WGRAD on a side stream next to the DGRAD chain
+
 # (cout, dilation, relu, pool_after) for the 13 convolutions of vgg_cfg["VGG16-OICR"]
 LAYERS = [(64, 1, True, False), (64, 1, True, True), (128, 1, True, False), (128, 1, True, True),
           (256, 1, True, False), (256, 1, True, False), (256, 1, True, True),
@@ -54,6 +56,18 @@ def wgrad(x_nhwc, dz_nhwc, w_shape, dil, strict):
         capi.conv3x3_wgrad_nhwc(xl, zh, dilation=dil, accumulate_into=dw, want_bias=False)
         db = dz_nhwc.sum((0, 1, 2))
     return dw.permute(0, 3, 1, 2).contiguous(), db          # [Cout,3,3,Cin] -> torch's [Cout,Cin,3,3]
+
+
+_side_streams = {}
+
+
+def _side_stream(device):
+    """One extra stream per device: the WGRAD of a layer only depends on that layer's dZ, so it runs beside the DGRAD
+    chain and fills the SMs the DGRAD's last partial wave leaves idle (304 tiles on 148 SMs = 2.05 waves)."""
+    s = _side_streams.get(device.index)
+    if s is None:
+        s = _side_streams[device.index] = torch.cuda.Stream(device=device)
+    return s
 
 
 class _VGGStackFn(Function):
@@ -96,6 +110,8 @@ class _VGGStackFn(Function):
         dz = g.contiguous()                             # gradient of layer n-1's pre-activation (no ReLU after conv5_3)
         if not ctx.strict:
             dz = capi.round_tf32_(dz.clone() if dz.data_ptr() == g.data_ptr() else dz)
+        main = torch.cuda.current_stream(dz.device)
+        side = _side_stream(dz.device) if OVERLAP_WGRAD else None
         for i in range(n - 1, ctx.first_train - 1, -1):
             cout, dil, relu, pool = LAYERS[i]
             if i == 0:
@@ -106,7 +122,17 @@ class _VGGStackFn(Function):
                 break
             xin = saved["in%d" % i]
             if ctx.needs_w[i]:
-                grads[2 * i], grads[2 * i + 1] = wgrad(xin, dz, ws[i].shape, dil, ctx.strict)
+                if side is None or i == ctx.first_train:
+                    grads[2 * i], grads[2 * i + 1] = wgrad(xin, dz, ws[i].shape, dil, ctx.strict)
+                else:
+                    side.wait_stream(main)              # dz (and everything before it) is ready
+                    with torch.cuda.stream(side):
+                        dw, db = wgrad(xin, dz, ws[i].shape, dil, ctx.strict)
+                    for t_ in (dz, xin):
+                        t_.record_stream(side)          # the caching allocator must not recycle them under the side stream
+                    for t_ in (dw, db):
+                        t_.record_stream(main)
+                    grads[2 * i], grads[2 * i + 1] = dw, db
             if i == ctx.first_train:
                 break
             # DGRAD: d(input of layer i).  The input is either layer i-1's post-ReLU output (mask fused in the
@@ -120,6 +146,8 @@ class _VGGStackFn(Function):
                 dz = _conv(dz, wd, None, dil, capi.CONV_MASK, ctx.strict, mask_src=xin)
             else:
                 dz = _conv(dz, wd, None, dil, 0, ctx.strict)
+        if side is not None:
+            main.wait_stream(side)                      # gradients are consumed (DDP hooks, optimizer) on the main stream
         return (None, None) + tuple(grads)
 
 

@@ -23,6 +23,12 @@ from . import registry
 from .sim_head import SupConLossV2, supcon_bank_loss
 
 
+def _gather(pooled, rows):
+    """pooled[rows]; a pooled tensor produced by forward_clean_and_aug routes the gradient through its own gather."""
+    g = getattr(pooled, "_odw_gather", None)
+    return g(rows) if g is not None else pooled.index_select(0, rows)
+
+
 def _host_labels(target):
     lab = target.get_field("labels_host") if target.has_field("labels_host") else target.get_field("labels")
     if isinstance(lab, torch.Tensor):
@@ -148,12 +154,12 @@ class RoIRegLossComputation(object):
             self.overflow = torch.zeros((1,), dtype=torch.float32, device=st.offA.device)
         rows = st.rowsA[:K].long()
         if self.batch_aug:
-            X = clean_pooled_feats.index_select(0, rows)
+            X = _gather(clean_pooled_feats, rows)
             aug = torch.cat([feature_extractor.drop_pool(X), feature_extractor.noise_pool(X)], dim=0)
         else:
             drops, noises = [], []
             for p in range(P):
-                Xp = clean_pooled_feats.index_select(0, rows[int(offA_h[p]):int(offA_h[p + 1])])
+                Xp = _gather(clean_pooled_feats, rows[int(offA_h[p]):int(offA_h[p + 1])])
                 drops.append(feature_extractor.drop_pool(Xp))
                 noises.append(feature_extractor.noise_pool(Xp))
             aug = torch.cat(drops + noises, dim=0)
@@ -171,7 +177,7 @@ class RoIRegLossComputation(object):
         kv = torch.clamp(k64, max=Kc)                             # rows that really exist in the padded batch
         ar = torch.arange(Kc, device=dev)
         rows = torch.where(ar < kv, st.rowsA[:Kc].long(), torch.zeros_like(ar))
-        X = clean_pooled_feats.index_select(0, rows)
+        X = _gather(clean_pooled_feats, rows)
         aug = torch.cat([feature_extractor.drop_pool(X, n_valid=kdev), feature_extractor.noise_pool(X)], dim=0)
         Epad = model_sim(feature_extractor.forward_neck(aug))     # [2Kc,128]
         j = torch.arange(2 * P * Ncap, device=dev)                # K <= P*Ncap always: every address the kernels form is in range

@@ -90,6 +90,7 @@ class VGG16FC67ROIFeatureExtractor(nn.Module):
             self.dropblock = DropBlock2D(block_size=3, drop_prob=0.3)
         self.sim_drop = DropBlock2D(block_size=1, drop_prob=0.3)
         self.noise_sampler = None      # test hook: callable(shape, device) -> N(0,1) tensor
+        self.fuse_clean_aug = True     # train: ROIPool + DropBlock into one [2R,...] batch, fc6/fc7 once
         if init_weights:
             for m in self.modules():
                 if isinstance(m, nn.Linear):
@@ -100,6 +101,34 @@ class VGG16FC67ROIFeatureExtractor(nn.Module):
         pooled_feat = self.pooler(x, proposals)
         x = self.classifier(pooled_feat.view(pooled_feat.shape[0], -1))
         return x, pooled_feat
+
+    def can_fuse_clean_aug(self):
+        from ..layers import ROIPool
+        return (self.fuse_clean_aug and self.training and hasattr(self, "dropblock") and self.dropblock.drop_prob > 0
+                and isinstance(self.pooler.poolers[0], ROIPool))
+
+    def forward_clean_and_aug(self, x, proposals):
+        """weak_head.py:107 + :111-112 in one pass: returns (clean_roi_feats, aug_roi_feats, clean_pooled_feats).
+        The same arithmetic as forward() followed by forward_neck(forward_dropblock(pooled)); the two fc6/fc7 passes
+        run as one batch, and clean_pooled_feats carries `_odw_gather(rows)` for the contrastive branch (its gradient
+        joins the single ROIPool backward instead of a dense zero-filled tensor)."""
+        from ..layers import gather_rows, pool_and_augment, split_rows
+        rois = self.pooler.convert_to_roi_format(proposals).float()
+        pool, db = self.pooler.poolers[0], self.dropblock
+        R = rois.shape[0]
+        ph, pw = pool.output_size if isinstance(pool.output_size, (tuple, list)) else (pool.output_size, pool.output_size)
+        gamma = db.drop_prob / (db.block_size ** 2)                         # drop_block.py:69-70
+        if db.centre_sampler is not None:
+            centres = db.centre_sampler(R, ph, pw, gamma, rois.device)
+        else:
+            centres = (torch.rand(R, ph, pw, device=rois.device) < gamma).float()
+        stash = {}
+        buf = pool_and_augment(x[0].float(), rois, (ph, pw), pool.spatial_scale, centres.contiguous(), db.block_size, stash)
+        feats = self.classifier(buf.view(2 * R, -1))
+        clean, aug = split_rows(feats, R)
+        pooled = buf.detach()[:R]
+        pooled._odw_gather = lambda rows: gather_rows(buf, rows, R, stash)
+        return clean, aug, pooled
 
     def forward_pooler(self, x, proposals):
         return self.pooler(x, proposals)

@@ -28,6 +28,16 @@ class ROIWeakRegHead(nn.Module):
         raise ValueError("DB.METHOD %r is outside the hot path (every shipped config uses 'dropblock')" % self.DB_METHOD)
 
     def forward(self, features, proposals, targets=None, model_cdb=None, iteration=None):
+        fe = self.feature_extractor
+        if self.training and self.DB_METHOD == "dropblock" and getattr(fe, "can_fuse_clean_aug", lambda: False)():
+            # :107 and :111-112 as ONE fc6/fc7 batch over [clean; DropBlock-augmented] pooled features
+            clean_roi_feats, aug_roi_feats, clean_pooled_feats = fe.forward_clean_and_aug(features, proposals)
+            sim_feature = self.model_sim(clean_roi_feats)                                             # :110
+            cls_score, det_score, ref_scores, ref_bbox_preds = self.predictor(aug_roi_feats, proposals)   # :113
+            loss_img, accuracy_img = self.loss_evaluator([cls_score], [det_score], ref_scores, ref_bbox_preds,
+                                                         sim_feature, clean_pooled_feats, fe, self.model_sim,
+                                                         proposals, targets)                          # :120
+            return aug_roi_feats, proposals, loss_img, accuracy_img
         clean_roi_feats, clean_pooled_feats = self.feature_extractor.forward(features, proposals)     # :107
         if not self.training:
             cls_score, det_score, ref_scores, ref_bbox_preds = self.predictor(clean_roi_feats, proposals)

@@ -262,3 +262,25 @@ def test_gemm_nt_tf32(capi, M, N, K):
     got = capi.gemm_nt_tf32(A.cuda(), B.cuda()).cpu()
     ref = (A.double() @ B.double().T).float()
     assert float((got - ref).abs().max()) <= 8e-3 * K ** 0.5          # TF32: operands truncated to 10 mantissa bits (2^-10 relative each)
+
+
+@pytest.mark.parametrize("B,C,H,W,R,S", [(2, 512, 76, 128, 600, 37), (1, 6, 152, 200, 90, 5), (2, 5, 20, 31, 64, 0)])
+def test_roi_pool_bwd_multi_source(capi, B, C, H, W, R, S):
+    """Several consumers of the pooled features (two dense gradients + gathered rows) scattered in one launch equal
+    the single-source backward of their sum."""
+    g = torch.Generator().manual_seed(R + S)
+    feat = torch.randn(B, C, H, W, generator=g).cuda()
+    rois = _rand_rois(g, B, H, W, R).cuda()
+    out, arg = capi.roi_pool_forward(feat, rois, 0.125, 7, 7)
+    q = lambda t: (t * 4).round() / 4                                   # exactly representable sums: bit-exact
+    g1, g2 = q(torch.randn(out.shape, generator=g)).cuda(), q(torch.randn(out.shape, generator=g)).cuda()
+    srows = torch.randint(0, R, (S,), generator=g).cuda() if S else None
+    sgrad = q(torch.randn((S, C, 7, 7), generator=g)).cuda() if S else None
+    got = capi.roi_pool_backward_multi(g1, g2, srows, sgrad, rois, arg, B, C, H, W)
+    tot = g1 + g2
+    if S:
+        tot.index_add_(0, srows, sgrad)
+    exp = capi.roi_pool_backward(tot, rois, arg, 7, 7, B, C, H, W)
+    assert got is not None and torch.equal(got.contiguous(), exp)
+    only1 = capi.roi_pool_backward_multi(g1, None, None, None, rois, arg, B, C, H, W)
+    assert torch.equal(only1.contiguous(), capi.roi_pool_backward(g1, rois, arg, 7, 7, B, C, H, W))
