@@ -286,12 +286,15 @@ def run_ours(args):
     tc_src = ("measured (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)"
               if "bf16_tflops_sustained" in peaks else "fallback 1500 TF/s dense bf16 (B200_PROFILING.md)")
     prof_steps = max(1, min(args.steps, 5))
+    from odwscl_b200.modeling import conv_stack
     torch.cuda.synchronize()
+    overlap, conv_stack.OVERLAP_WGRAD = conv_stack.OVERLAP_WGRAD, False    # one kernel at a time: its own duration
     capi.profile = []
     for _ in range(prof_steps):
         resident_step()
     torch.cuda.synchronize()
     prof, capi.profile = capi.profile, None
+    conv_stack.OVERLAP_WGRAD = overlap
     agg = {}
     for name, work, e0, e1 in prof:
         a = agg.setdefault(name, {"ms": 0.0, "n": 0, "work": 0.0, "kind": None})
@@ -329,9 +332,10 @@ def run_ours(args):
         if roofline["bound"] == "tensor":
             roofline["note"] = ("TF32 tcgen05 kernel (fp32 storage); the contract's peak is the measured dense bf16 rate, "
                                 "TF32 issues at half of it: frac_of_tf32_rate = %.3f" % (2 * roofline["frac"]))
-        roofline["timing"] = "CUDA events around each launch on its stream, live inside %d resident steps" % prof_steps
-        for k in ("odwscl_roi_pool_fwd_nhwc_f32", "odwscl_roi_pool_bwd_nhwc_f32", "odwscl_conv3x3_wgrad_nhwc_tf32",
-                  "odwscl_conv3x3_nhwc_tf32"):
+        roofline["timing"] = ("CUDA events around each launch on its stream, live inside %d resident steps "
+                              "(WGRAD side-stream overlap off for these steps so durations are per kernel)" % prof_steps)
+        for k in ("odwscl_roi_pool_fwd_nhwc_f32", "odwscl_roi_pool_bwd_nhwc_f32", "odwscl_roi_pool_bwd_nhwc_multi_f32",
+                  "odwscl_conv3x3_wgrad_nhwc_tf32", "odwscl_conv3x3_nhwc_tf32"):
             if k != roofline["kernel"] and entry(k):
                 roofline[k.replace("odwscl_", "")] = entry(k)
 

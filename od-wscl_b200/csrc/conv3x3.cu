@@ -532,6 +532,149 @@ int launch_wgrad(const float* x, const float* dz, int B, int H, int W, int Cin, 
   return 0;
 }
 
+// CTA-pair WGRAD (cta_group::2) for Cout % 256 == 0 and Cin % 256 == 0: the pair owns 256 output channels x 256 input
+// channels of one tap; each CTA stages its own 128 dZ channels and HALF of the X channels (same shared-memory
+// argument as conv3x3_tf32_2cta_kernel), the leader issues M = 256 MMAs, each CTA reduces its 128 accumulator rows.
+template <int STAGES>
+__global__ void __launch_bounds__(192, 1)
+conv3x3_wgrad_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_constant__ CUtensorMap map_x,
+                               float* __restrict__ dw, int H, int W, int B, int Cin, int Cout, int dil,
+                               int chunks_per_cta) {
+  constexpr int BN = 256;
+  constexpr int A_BYTES = 4 * kWgBox, B_BYTES = (BN / 2 / 32) * kWgBox, STAGE_BYTES = A_BYTES + B_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar;
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = tc::cluster_ctarank();
+  const int co_tiles = Cout / kBM;                             // even; adjacent blockIdx.x = adjacent Cout tiles
+  const int co0 = (blockIdx.x % co_tiles) * kBM, ci0 = (blockIdx.x / co_tiles) * BN;
+  const int tap = blockIdx.y;
+  const int r = tap / 3, q3 = tap - 3 * r;
+  const int cpr = (W + kWgPix - 1) / kWgPix;
+  const int total_chunks = B * H * cpr;
+  const int c_begin = blockIdx.z * chunks_per_cta;
+  const int c_end = min(total_chunks, c_begin + chunks_per_cta);
+  const int kiters = max(c_end - c_begin, 0);                  // identical in both CTAs of the pair (same blockIdx.z)
+
+  if (warp == 0 && tc::elect_one()) {
+    tc::tma_prefetch_desc(&map_dz);
+    tc::tma_prefetch_desc(&map_x);
+    for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+    tc::mbar_init(&tmem_full_bar, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc_2sm(&tmem_base_s, BN);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::cluster_sync_all();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  if (kiters > 0) {
+    if (warp == 0) {
+      if (tc::elect_one()) {
+        int c = c_begin;
+        int wc = c % cpr, hb = c / cpr;
+        int h = hb % H, b = hb / H;
+        for (int it = 0; it < kiters; ++it) {
+          const int s = it % STAGES;
+          tc::mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+          if (crank == 0) tc::mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
+          uint8_t* a = tiles + (size_t)s * STAGE_BYTES;
+          const int w0 = wc * kWgPix;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) tc::tma_load_4d_2sm(a + j * kWgBox, &map_dz, &full_bar[s], co0 + 32 * j, w0, h, b);
+#pragma unroll
+          for (int j = 0; j < BN / 2 / 32; ++j)
+            tc::tma_load_4d_2sm(a + A_BYTES + j * kWgBox, &map_x, &full_bar[s], ci0 + (int)crank * (BN / 2) + 32 * j,
+                                w0 + (q3 - 1) * dil, h + (r - 1) * dil, b);
+          if (++wc == cpr) { wc = 0; if (++h == H) { h = 0; ++b; } }
+        }
+      }
+    } else if (warp == 1) {
+      if (crank == 0 && tc::elect_one()) {
+        constexpr uint32_t idesc = tc::umma_idesc_tf32_mn(2 * kBM, BN);
+        for (int it = 0; it < kiters; ++it) {
+          const int s = it % STAGES;
+          tc::mbar_wait(&full_bar[s], (it / STAGES) & 1);
+          tc::tc_fence_after();
+          const uint32_t a = tc::smem_u32(tiles + (size_t)s * STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < kWgPix / tc::kUmmaK; ++k) {
+            const uint64_t ad = tc::umma_desc_mn_sw128_32b(a + k * 1024, kWgBox, 512);
+            const uint64_t bd = tc::umma_desc_mn_sw128_32b(a + A_BYTES + k * 1024, kWgBox, 512);
+            tc::umma_tf32_2sm(tmem_base, ad, bd, idesc, (it | k) != 0);
+          }
+          tc::umma_commit_2sm_mc(&empty_bar[s], 3);
+        }
+        tc::umma_commit_2sm_mc(&tmem_full_bar, 3);
+      }
+    } else {
+      const int q = warp & 3;
+      const int co = co0 + q * 32 + lane;
+      tc::mbar_wait(&tmem_full_bar, 0);
+      tc::tc_fence_after();
+      float v[32];
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, v);
+        tc::tmem_ld_wait();
+        if (co >= Cout) continue;
+        float* dst = dw + ((size_t)co * 9 + tap) * Cin + ci0 + c * 32;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * j), "f"(v[4 * j]), "f"(v[4 * j + 1]),
+                       "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::cluster_sync_all();
+  if (warp == 1) tc::tmem_dealloc_2sm(tmem_base, BN);
+}
+
+static int launch_wgrad_2cta(const float* x, const float* dz, int B, int H, int W, int Cin, int Cout, int dil, float* dw,
+                             cudaStream_t st) {
+  constexpr int STAGES = 6;
+  CUtensorMap mz, mx;
+  const uint32_t box[4] = {32, (uint32_t)kWgPix, 1, 1};
+  const uint64_t dzd[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+  const uint64_t dzs[3] = {(uint64_t)Cout * 4, (uint64_t)W * Cout * 4, (uint64_t)H * W * Cout * 4};
+  int rc = tc::make_tmap_f32(&mz, dz, 4, dzd, dzs, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  if (rc) return rc;
+  const uint64_t dx[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+  const uint64_t sx[3] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4};
+  rc = tc::make_tmap_f32(&mx, x, 4, dx, sx, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  if (rc) return rc;
+  const int tiles = (Cout / kBM) * (Cin / 256);
+  const int total_chunks = B * H * odw_cdiv(W, kWgPix);
+  int splits = max(1, (ODW_NUM_SMS) / (tiles * 9));
+  splits = min(splits, total_chunks);
+  const int per = odw_cdiv(total_chunks, splits);
+  splits = odw_cdiv(total_chunks, per);
+  const int smem = STAGES * (4 + 4) * kWgBox + 1024;
+  auto kern = conv3x3_wgrad_tf32_2cta_kernel<STAGES>;
+  ODW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  ODW_CUDA(cudaMemsetAsync(dw, 0, (size_t)Cout * 9 * Cin * sizeof(float), st));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(tiles, 9, splits);
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ODW_CUDA(cudaLaunchKernelEx(&cfg, kern, mz, mx, dw, H, W, B, Cin, Cout, dil, per));
+  return 0;
+}
+
 // db[co] = sum_pixels dz[pixel, co]
 __global__ void bias_grad_kernel(const float* __restrict__ dz, long long P, int C, float* __restrict__ db) {
   // block = 32 channels x 8 pixel lanes; grid.x = channel groups, grid.y = pixel slabs
@@ -709,6 +852,8 @@ ODW_API int odwscl_conv3x3_wgrad_nhwc_tf32(const float* x, const float* dz, int 
     bias_grad_kernel<<<grid, 256, 0, st>>>(dz, P, Cout, db);
     ODW_LAUNCH_CHECK();
   }
+  if (Cin % 256 == 0 && Cout % 256 == 0 && conv_env("ODWSCL_CONV_2CTA", 1) != 0)
+    return launch_wgrad_2cta(x, dz, B, H, W, Cin, Cout, dilation, dw_krsc, st);
   if (Cin % 256 == 0) return launch_wgrad<256>(x, dz, B, H, W, Cin, Cout, dilation, dw_krsc, st);
   if (Cin % 128 == 0) return launch_wgrad<128>(x, dz, B, H, W, Cin, Cout, dilation, dw_krsc, st);
   if (Cin % 64 == 0) return launch_wgrad<64>(x, dz, B, H, W, Cin, Cout, dilation, dw_krsc, st);

@@ -59,6 +59,20 @@ dropblock_apply_kernel(const float* __restrict__ x, const float* __restrict__ ce
   __syncthreads();
   const size_t base = (size_t)r * C * cells;
   const int n = C * cells;
+  if ((n & 3) == 0) {                                        // 16-byte streaming loads / stores ((r*n) % 4 == 0)
+    const float4* x4 = reinterpret_cast<const float4*>(x + base);
+    float4* y4 = reinterpret_cast<float4*>(y + base);
+    for (int t = threadIdx.x; t < n / 4; t += blockDim.x) {
+      float4 v = __ldcs(x4 + t);
+      const int k = (4 * t) % cells;                         // 4 consecutive bins, wrapping into the next channel
+      v.x *= s_bm[k];
+      v.y *= s_bm[k + 1 < cells ? k + 1 : k + 1 - cells];
+      v.z *= s_bm[k + 2 < cells ? k + 2 : k + 2 - cells];
+      v.w *= s_bm[k + 3 < cells ? k + 3 : k + 3 - cells];
+      __stcs(y4 + t, v);
+    }
+    return;
+  }
   for (int t = threadIdx.x; t < n; t += blockDim.x) {
     const float v = __ldcs(x + base + t) * s_bm[t % cells];
     __stcs(y + base + t, v);
