@@ -26,7 +26,7 @@ if [[ $ST == *l* ]]; then
   echo "launch list rc=$?"; wc -l $OUT/launches.csv
 fi
 if [[ $ST == *n* ]]; then
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"roi_pool_fwd_nhwc7|roi_pool_bwd|nchw_to_nhwc" -c 6 \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"roi_pool_fwd_nhwc7|roi_pool_bwd" -s 6 -c 2 \
       -o $OUT/prof_roipool -f python scripts/run_roipool_once.py > $OUT/ncu_full.log 2>&1
   echo "ncu full rc=$?"; ls -la $OUT
 fi
@@ -41,4 +41,10 @@ if [[ $ST == *c* ]]; then
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:"conv3x3_tf32_2cta_kernel" -s 42 -c 1 \
       -o $OUT/prof_conv_b -f python scripts/bench_conv.py 2 >> $OUT/ncu_conv.log 2>&1
   echo "ncu conv rc=$?"; ls -la $OUT
+fi
+if [[ $ST == *w* ]]; then
+  # the CTA-pair WGRAD at the conv4_2 / conv5_x shape
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:"conv3x3_wgrad_tf32_2cta_kernel" -s 3 -c 1 \
+      -o $OUT/prof_wgrad -f python scripts/run_wgrad_once.py > $OUT/ncu_wgrad.log 2>&1
+  echo "ncu wgrad rc=$?"
 fi
