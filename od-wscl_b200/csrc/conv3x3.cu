@@ -318,6 +318,254 @@ static int launch_conv_2cta(const CUtensorMap& mx, const CUtensorMap& mw, const 
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// PERSISTENT CTA-pair version with a stream-K schedule.  The one-tile-per-pair kernel above loses two things the
+// profile shows: the epilogue / pipeline fill of each tile is not overlapped with the next tile's MMAs (tensor pipe
+// 77 % busy while active), and 304 tiles on 148 SMs run as 3 waves instead of 2.05 (51 % busy over the elapsed time).
+// Here NP resident pairs split the linearised (pair-tile, k-iteration) space into NP equal contiguous ranges, so every
+// SM gets the same number of MMAs; a pair-tile that straddles two ranges is finished by the pair holding its HEAD
+// (k = 0 ..), which adds the TAIL partial the neighbouring pair left in a global workspace (that pair computed it as
+// its FIRST work item, long before).  Accumulators are double-buffered in TMEM (2 x 256 columns): the epilogue
+// warps drain tile i while the MMA thread is already accumulating tile i+1.
+struct ConvSkParams {
+  int n_ptiles;        // pair-tiles = (pixel tiles / 2) * (Cout / 256)
+  int n_ntiles;        // Cout / 256
+  int kiters;          // 9 * Cin / 32
+  int per_pair;        // k-iterations per pair (ceil)
+  float* ws;           // [NP][2][128][256] partial accumulators
+  int* flags;          // [NP][2], zeroed before the launch
+};
+
+template <int STAGES>
+__global__ void __launch_bounds__(192, 1)
+conv3x3_tf32_2cta_sk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                            const float* __restrict__ bias, const float* __restrict__ mask_src, float* __restrict__ y,
+                            int H, int W, int Cin, int Cout, int tw_log2, int tiles_w, int tiles_h, int dil, int flags,
+                            const ConvSkParams sk) {
+  constexpr int BN = 256, A_BYTES = kBM * tc::kTileKBytes, B_BYTES = (BN / 2) * tc::kTileKBytes;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = tc::cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int TW = 1 << tw_log2, TH = kBM >> tw_log2;
+  const int cchunks = Cin / tc::kTileK;
+  const long long total = (long long)sk.n_ptiles * sk.kiters;
+  const long long g_begin = (long long)pair * sk.per_pair;
+  const long long g_end = min(total, g_begin + sk.per_pair);
+
+  if (warp == 0 && tc::elect_one()) {
+    tc::tma_prefetch_desc(&map_x);
+    tc::tma_prefetch_desc(&map_w);
+    for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tmem_full_bar[i], 1); tc::mbar_init(&tmem_empty_bar[i], 256); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc_2sm(&tmem_base_s, 2 * BN);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::cluster_sync_all();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  // decode of a pair-tile: n-tile fastest, then the pair of adjacent pixel tiles (this CTA takes 2*m + rank)
+  auto tile_coords = [&](int pt, int& b, int& h0, int& w0, int& n0) {
+    n0 = (pt % sk.n_ntiles) * BN;
+    int t = (pt / sk.n_ntiles) * 2 + (int)crank;
+    const int tx = t % tiles_w; t /= tiles_w;
+    const int ty = t % tiles_h;
+    b = t / tiles_h;
+    w0 = tx * TW; h0 = ty * TH;
+  };
+
+  if (warp == 0) {
+    if (tc::elect_one()) {
+      int it = 0;
+      for (long long g = g_begin; g < g_end;) {
+        const int pt = (int)(g / sk.kiters), k0 = (int)(g - (long long)pt * sk.kiters);
+        const int k1 = (int)min((long long)sk.kiters, (long long)k0 + (g_end - g));
+        int b, h0, w0, n0;
+        tile_coords(pt, b, h0, w0, n0);
+        int tap = k0 / cchunks, cc = k0 - tap * cchunks;
+        for (int kk = k0; kk < k1; ++kk, ++it) {
+          const int s = it % STAGES;
+          tc::mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+          if (crank == 0) tc::mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
+          uint8_t* a = tiles + (size_t)s * STAGE_BYTES;
+          const int r = tap / 3, q = tap - 3 * r;
+          tc::tma_load_4d_2sm(a, &map_x, &full_bar[s], cc * tc::kTileK, w0 + (q - 1) * dil, h0 + (r - 1) * dil, b);
+          tc::tma_load_2d_2sm(a + A_BYTES, &map_w, &full_bar[s], tap * Cin + cc * tc::kTileK, n0 + (int)crank * (BN / 2));
+          if (++cc == cchunks) { cc = 0; ++tap; }
+        }
+        g += k1 - k0;
+      }
+    }
+  } else if (warp == 1) {
+    if (crank == 0 && tc::elect_one()) {
+      constexpr uint32_t idesc = tc::umma_idesc_tf32(2 * kBM, BN);
+      int it = 0, item = 0;
+      for (long long g = g_begin; g < g_end; ++item) {
+        const int pt = (int)(g / sk.kiters), k0 = (int)(g - (long long)pt * sk.kiters);
+        const int k1 = (int)min((long long)sk.kiters, (long long)k0 + (g_end - g));
+        const int buf = item & 1;
+        tc::mbar_wait(&tmem_empty_bar[buf], ((item >> 1) & 1) ^ 1);     // both CTAs drained this accumulator
+        tc::tc_fence_after();
+        const uint32_t acc = tmem_base + buf * BN;
+        for (int kk = k0; kk < k1; ++kk, ++it) {
+          const int s = it % STAGES;
+          tc::mbar_wait(&full_bar[s], (it / STAGES) & 1);
+          tc::tc_fence_after();
+          const uint32_t a = tc::smem_u32(tiles + (size_t)s * STAGE_BYTES);
+          const uint64_t ad = tc::umma_desc_sw128(a), bd = tc::umma_desc_sw128(a + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < tc::kTileK / tc::kUmmaK; ++k)
+            tc::umma_tf32_2sm(acc, ad + 2 * k, bd + 2 * k, idesc, (kk != k0) || (k != 0));
+          tc::umma_commit_2sm_mc(&empty_bar[s], 3);
+        }
+        tc::umma_commit_2sm_mc(&tmem_full_bar[buf], 3);
+        g += k1 - k0;
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int item = 0;
+    float v[32];
+    for (long long g = g_begin; g < g_end; ++item) {
+      const int pt = (int)(g / sk.kiters), k0 = (int)(g - (long long)pt * sk.kiters);
+      const int k1 = (int)min((long long)sk.kiters, (long long)k0 + (g_end - g));
+      g += k1 - k0;
+      const int buf = item & 1;
+      int b, h0, w0, n0;
+      tile_coords(pt, b, h0, w0, n0);
+      const int h = h0 + (row >> tw_log2), w = w0 + (row & (TW - 1));
+      const bool valid = (h < H) && (w < W) && b * tiles_h * tiles_w + (h0 / TH) * tiles_w + (w0 / TW) < 2 * (sk.n_ptiles / sk.n_ntiles);
+      const size_t pix = ((size_t)b * H + h) * W + w;
+      const bool tail_part = k0 > 0;                      // this pair's FIRST item: the rest of a tile another pair heads
+      const bool head_part = k0 == 0 && k1 < sk.kiters;   // this pair's LAST item: the next pair holds the tail
+      tc::mbar_wait(&tmem_full_bar[buf], (item >> 1) & 1);
+      tc::tc_fence_after();
+      float* part = sk.ws + (((size_t)(tail_part ? pair : pair + 1) * 2 + crank) * kBM + row) * BN;
+      if (head_part) {                                    // the neighbour finished its tail long ago; acquire its data
+        const int* f = sk.flags + (pair + 1) * 2 + crank;
+        while (*reinterpret_cast<const volatile int*>(f) == 0) __nanosleep(64);
+        __threadfence();
+      }
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + c * 32, v);
+        tc::tmem_ld_wait();
+        if (tail_part) {
+          float4* dstp = reinterpret_cast<float4*>(part + c * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dstp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          continue;
+        }
+        const int co = n0 + c * 32;
+        if (!valid || co >= Cout) continue;
+        float4* dst = reinterpret_cast<float4*>(y + pix * Cout + co);
+        const float4* msk = reinterpret_cast<const float4*>(mask_src + pix * Cout + co);
+        const float4* prt = reinterpret_cast<const float4*>(part + c * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          if (head_part) {
+            const float4 pp = __ldcg(prt + j);
+            o.x += pp.x; o.y += pp.y; o.z += pp.z; o.w += pp.w;
+          }
+          if (bias != nullptr) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + co) + j);
+            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+          }
+          if (flags & kAccum) {
+            const float4 p = dst[j];
+            o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+          }
+          if (flags & kRelu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          if (flags & kMask) {
+            const float4 mm = __ldg(msk + j);
+            o.x = mm.x > 0.f ? o.x : 0.f; o.y = mm.y > 0.f ? o.y : 0.f; o.z = mm.z > 0.f ? o.z : 0.f; o.w = mm.w > 0.f ? o.w : 0.f;
+          }
+          if (flags & kRound) { o.x = rna_tf32(o.x); o.y = rna_tf32(o.y); o.z = rna_tf32(o.z); o.w = rna_tf32(o.w); }
+          dst[j] = o;
+        }
+      }
+      tc::tc_fence_before();
+      tc::mbar_arrive_leader(&tmem_empty_bar[buf]);       // 128 threads x 2 CTAs -> the leader may reuse this accumulator
+      if (tail_part) {                                    // publish the partial: all 128 rows written, then the flag
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 64) {
+          __threadfence();
+          atomicExch(sk.flags + pair * 2 + crank, 1);
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::cluster_sync_all();
+  if (warp == 1) tc::tmem_dealloc_2sm(tmem_base, 2 * BN);
+}
+
+static void* g_sk_ws = nullptr;          // [74][2][128][256] fp32 partials + flags, allocated once per process
+static size_t g_sk_ws_bytes = 0;
+
+template <int STAGES>
+static int launch_conv_2cta_sk(const CUtensorMap& mx, const CUtensorMap& mw, const float* bias, const float* msk, float* y,
+                               int H, int W, int Cin, int Cout, int best_log2, int tiles_w, int tiles_h, int total_tiles,
+                               int dil, int flags, cudaStream_t st, bool* used) {
+  *used = false;
+  const int smem = STAGES * (kBM + 128) * tc::kTileKBytes + 1024;
+  auto kern = conv3x3_tf32_2cta_sk_kernel<STAGES>;
+  ODW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  ODW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 0));
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  static int max_pairs = -1;             // pairs that are guaranteed co-resident (the schedule spins on a neighbour)
+  if (max_pairs < 0) {
+    cfg.gridDim = dim3(2 * (ODW_NUM_SMS / 2));
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) n = 0;
+    max_pairs = n;
+  }
+  ConvSkParams sk;
+  sk.n_ntiles = Cout / 256;
+  sk.n_ptiles = (total_tiles / 2) * sk.n_ntiles;
+  sk.kiters = 9 * (Cin / tc::kTileK);
+  const int np = min(max_pairs, min(ODW_NUM_SMS / 2, sk.n_ptiles));
+  if (np < 8) return 0;                  // not enough resident pairs: caller uses the one-tile-per-pair kernel
+  const long long total = (long long)sk.n_ptiles * sk.kiters;
+  sk.per_pair = (int)((total + np - 1) / np);
+  if (sk.per_pair < sk.kiters) return 0; // a tile would span three pairs: not handled
+  const size_t need = (size_t)(np + 1) * 2 * kBM * 256 * sizeof(float) + (size_t)(np + 2) * 2 * sizeof(int);
+  if (g_sk_ws_bytes < need) {
+    if (g_sk_ws) cudaFree(g_sk_ws);
+    ODW_CUDA(cudaMalloc(&g_sk_ws, need));
+    g_sk_ws_bytes = need;
+  }
+  sk.ws = reinterpret_cast<float*>(g_sk_ws);
+  sk.flags = reinterpret_cast<int*>(reinterpret_cast<char*>(g_sk_ws) + (size_t)(np + 1) * 2 * kBM * 256 * sizeof(float));
+  ODW_CUDA(cudaMemsetAsync(sk.flags, 0, (size_t)(np + 2) * 2 * sizeof(int), st));
+  cfg.gridDim = dim3(2 * np);
+  ODW_CUDA(cudaLaunchKernelEx(&cfg, kern, mx, mw, bias, msk, y, H, W, Cin, Cout, best_log2, tiles_w, tiles_h, dil, flags, sk));
+  *used = true;
+  return 0;
+}
+
 // ODWSCL_CONV_CLUSTER=2 turns the 2-CTA weight multicast on, ODWSCL_CONV_MT=1 turns the two-accumulator tiles off
 // (A/B measurements)
 static int conv_env(const char* name, int dflt) {
@@ -382,9 +630,16 @@ int launch_conv(const float* x, int B, int H, int W, int Cin, const float* wk, c
   if (rc) return rc;
   const float* msk = mask_src ? mask_src : y;
   if constexpr (BN == 256) {
-    if (pair)
+    if (pair) {
+      if (conv_env("ODWSCL_CONV_PERSIST", 1) != 0) {
+        bool used = false;
+        rc = launch_conv_2cta_sk<6>(mx, mw, bias, msk, y, H, W, Cin, Cout, best_log2, tiles_w, tiles_h, total_tiles, dil,
+                                    flags, st, &used);
+        if (rc != 0 || used) return rc;
+      }
       return launch_conv_2cta<6>(mx, mw, bias, msk, y, H, W, Cin, Cout, best_log2, tiles_w, tiles_h, total_tiles, dil,
                                  flags, st);
+    }
     if (mt2)
       return launch_conv_inst<BN, 3, 1, 2>(mx, mw, bias, msk, y, H, W, Cin, Cout, best_log2, tiles_w, tiles_h, total_tiles,
                                            dil, flags, st);

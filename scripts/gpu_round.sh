@@ -21,7 +21,7 @@ if [[ $ST == *b* ]]; then
   cat $OUT/bench.json; tail -5 $OUT/bench.err
 fi
 if [[ $ST == *l* ]]; then
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 4000 --csv --log-file $OUT/launches.csv \
+  timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --profile-from-start off -c 4000 --csv --log-file $OUT/launches.csv \
       python bench.py --steps 2 --warmup 3 --no-cpu-baseline --profile-range > $OUT/bench_under_ncu.log 2>&1
   echo "launch list rc=$?"; wc -l $OUT/launches.csv
 fi
