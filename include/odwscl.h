@@ -30,6 +30,7 @@ extern "C" {
 #define ODWSCL_VERSION 100
 #define ODWSCL_EINVAL (-1)   /* bad argument (null pointer, negative size, unsupported shape) */
 #define ODWSCL_ENOWS  (-2)   /* workspace too small */
+#define ODWSCL_SUPCON_SPLITS 8   /* column splits of the SupCon tile kernels (stats scratch size) */
 #define ODWSCL_SIM_DIM 128   /* embedding width of Sim_Net (sim_head/sim_net.py:13-16) */
 
 typedef void* odwscl_stream_t;
@@ -138,7 +139,9 @@ int odwscl_bank_assemble(const int32_t* pair_img, const int32_t* pair_cls, int P
 /* ---- A12: SupConLossV2 forward / backward (sim_head/sim_loss.py:49-80), fused: the M x M
  * similarity tile product, masked exp row sums and the weighted log ratio never leave the SM.
  * V = [F ; E] addressed through row_src; M read from device (M_dev) so no host sync is needed.
- * stats [Mcap,4] fp32 (row max, pos sum, all sum, row loss); loss_out [1] fp32 = mean_r(...). */
+ * stats [(1 + ODWSCL_SUPCON_SPLITS) * Mcap, 4] fp32: rows [0,Mcap) = (row max, pos sum, all sum, row loss), the rest is
+ * scratch for the per-column-split partials (the column loop is split over ODWSCL_SUPCON_SPLITS CTAs per row tile and
+ * merged in a fixed order); loss_out [1] fp32 = mean_r(...). */
 int odwscl_supcon_fwd_f32(const float* F, const float* E, int R, const int32_t* row_src,
                           const int32_t* row_lab, const float* row_w, const int32_t* M_dev, int Mcap,
                           float inv_temp, float* stats, float* loss_out, odwscl_stream_t stream);

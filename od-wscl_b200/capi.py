@@ -317,6 +317,7 @@ def dropblock(x, centres, block, scale_io=None, n_valid=None, out=None):
 
 # ---------------------------------------------------------------- conv stack (NHWC)
 CONV_RELU, CONV_ACCUM, CONV_MASK, CONV_ROUND = 1, 2, 4, 8
+SUPCON_SPLITS = 8          # ODWSCL_SUPCON_SPLITS in include/odwscl.h
 
 
 def conv3x3_nhwc(x, w_krsc, bias, dilation=1, flags=0, mask_src=None, out=None):
@@ -464,7 +465,7 @@ def bank_assemble(st, num_fg_classes, Mcap):
 
 def supcon_forward(F, E, row_src, row_lab, row_w, M_dev, Mcap, inv_temp):
     dev = F.device
-    stats = torch.empty((max(Mcap, 1), 4), dtype=torch.float32, device=dev)
+    stats = torch.empty(((1 + SUPCON_SPLITS) * max(Mcap, 1), 4), dtype=torch.float32, device=dev)   # merged rows + split scratch
     loss = torch.zeros((1,), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         _call("odwscl_supcon_fwd_f32", _ptr(F), _ptr(E), F.shape[0], _ptr(row_src), _ptr(row_lab), _ptr(row_w),

@@ -430,8 +430,12 @@ od_layer_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ im
   int64_t* lab = labels + (size_t)i * R + off;
   float* wts = weights + (size_t)i * R + off;
   float4* tgt = targets + (size_t)i * R + off;
+  // gridDim.y CTAs share one (image, branch): each labels a contiguous slice of the proposals against ALL pseudo-GT
+  // boxes (the class-argmax prelude is recomputed per CTA: N loads per class, negligible)
+  const int slice = (N + gridDim.y - 1) / gridDim.y;
+  const int j_lo = min(N, (int)blockIdx.y * slice), j_hi = min(N, j_lo + slice);
   if (q_lo == q_hi) {                               // no positive class: all background, zero weight
-    for (int j = threadIdx.x; j < N; j += blockDim.x) { lab[j] = 0; wts[j] = 0.f; tgt[j] = make_float4(0, 0, 0, 0); }
+    for (int j = j_lo + threadIdx.x; j < j_hi; j += blockDim.x) { lab[j] = 0; wts[j] = 0.f; tgt[j] = make_float4(0, 0, 0, 0); }
     return;
   }
   // argmax of each class column on the progressively zeroed score matrix
@@ -449,7 +453,7 @@ od_layer_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ im
     __syncthreads();
   }
   // running first-max over GT chunks
-  const int per = (N + blockDim.x - 1) / blockDim.x;      // proposals per thread (<= 8 for N <= 8192)
+  const int per = (j_hi - j_lo + blockDim.x - 1) / blockDim.x;      // proposals per thread (<= 8 for N <= 8192)
   float best[8]; int barg[8]; float bsc[8]; int bcl[8]; float4 bgt[8];
 #pragma unroll
   for (int u = 0; u < 8; ++u) { best[u] = -1.f; barg[u] = 0; bsc[u] = 0.f; bcl[u] = 0; bgt[u] = make_float4(0, 0, 0, 0); }
@@ -479,8 +483,8 @@ od_layer_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ im
     __syncthreads();
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const int j = threadIdx.x + u * blockDim.x;
-      if (u < per && j < N) {
+      const int j = j_lo + threadIdx.x + u * blockDim.x;
+      if (u < per && j < j_hi) {
         const float4 pj = __ldg(boxes + off + j);
         for (int g = 0; g < filled; ++g) {
           const float v = odw_iou(pj, g_box[g], 1.f);
@@ -491,8 +495,8 @@ od_layer_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ im
   }
 #pragma unroll
   for (int u = 0; u < 8; ++u) {
-    const int j = threadIdx.x + u * blockDim.x;
-    if (u < per && j < N) {
+    const int j = j_lo + threadIdx.x + u * blockDim.x;
+    if (u < per && j < j_hi) {
       const float4 pj = __ldg(boxes + off + j);
       lab[j] = best[u] <= fg_thr ? 0 : (int64_t)bcl[u];           // :183 (le)
       wts[j] = bsc[u];
@@ -597,7 +601,8 @@ ODW_API int odwscl_od_layer_f32(const float* boxes, const int32_t* img_off, int 
   if (B == 0 || R == 0) return 0;
   if (!boxes || !img_off || !s0 || !s1 || !s2 || !labels || !weights || !targets) return ODWSCL_EINVAL;
   if (P > 0 && (!pair_img || !pair_cls || !inst || !inst_cnt)) return ODWSCL_EINVAL;
-  od_layer_kernel<<<B * 3, kCtaThreads, 0, (cudaStream_t)stream>>>(
+  const int nsplit = max(1, min(16, odw_cdiv(Ncap, 128)));     // 128 proposals per CTA: every thread-proposal loop is short
+  od_layer_kernel<<<dim3(B * 3, nsplit), kCtaThreads, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const float4*>(boxes), img_off, R, C, s0, s1, s2, pair_img, pair_cls, P, Ncap, inst,
       inst_cnt, fg_thr, labels, weights, reinterpret_cast<float4*>(targets));
   ODW_LAUNCH_CHECK();

@@ -21,6 +21,7 @@ constexpr int kD = ODWSCL_SIM_DIM;   // 128
 constexpr int kT = 64;               // tile rows / cols
 constexpr int kLd = kT + 4;          // k-major leading dimension (floats), keeps float4 alignment
 constexpr int kThreads = 256;
+constexpr int kSplit = ODWSCL_SUPCON_SPLITS;   // column splits: a bank of ~1100 rows is only 18 row tiles -> 18 x 8 CTAs
 
 __device__ __forceinline__ const float* bank_row(const float* F, const float* E, int R, int src) {
   return src < R ? F + (size_t)src * kD : E + (size_t)(src - R) * kD;
@@ -71,7 +72,7 @@ __global__ void __launch_bounds__(kThreads, 2)
 supcon_fwd_kernel(const float* __restrict__ F, const float* __restrict__ E, int R,
                   const int32_t* __restrict__ row_src, const int32_t* __restrict__ row_lab,
                   const float* __restrict__ row_w, const int32_t* __restrict__ M_dev, int Mcap, float inv_temp,
-                  float4* __restrict__ stats) {
+                  float4* __restrict__ part) {
   extern __shared__ __align__(16) float smem_f[];
   float* sA = smem_f;
   float* sB = smem_f + kD * kLd;
@@ -79,6 +80,9 @@ supcon_fwd_kernel(const float* __restrict__ F, const float* __restrict__ E, int 
   const int M = min(*M_dev, Mcap);
   const int r0 = blockIdx.x * kT;
   if (r0 >= M) return;
+  // this CTA's share of the column tiles (blockIdx.y of kSplit); partial (max, pos, all) go to part[split][row]
+  const int per_split = ((M + kT - 1) / kT + kSplit - 1) / kSplit * kT;
+  const int c_begin = blockIdx.y * per_split, c_end = min(M, c_begin + per_split);
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
   load_tile_kmajor(sA, F, E, R, row_src, r0, M);
   int my_lab[4];
@@ -88,7 +92,7 @@ supcon_fwd_kernel(const float* __restrict__ F, const float* __restrict__ E, int 
 #pragma unroll
   for (int u = 0; u < 4; ++u) { m[u] = -INFINITY; ps[u] = 0.f; as[u] = 0.f; }
 
-  for (int c0 = 0; c0 < M; c0 += kT) {
+  for (int c0 = c_begin; c0 < c_end; c0 += kT) {
     __syncthreads();
     load_tile_kmajor(sB, F, E, R, row_src, c0, M);
     if (threadIdx.x < kT) s_lab[threadIdx.x] = (c0 + threadIdx.x < M) ? __ldg(row_lab + c0 + threadIdx.x) : -2;
@@ -133,20 +137,26 @@ supcon_fwd_kernel(const float* __restrict__ F, const float* __restrict__ E, int 
       merge_stats(m[u], ps[u], as[u], m2, p2, a2);
     }
     const int r = r0 + ty * 4 + u;
-    if (tx == 0 && r < M) {
-      const float lr = -logf(ps[u] / as[u]) * __ldg(row_w + r);     // sim_loss.py:76-78
-      stats[r] = make_float4(m[u], ps[u], as[u], lr);
-    }
+    if (tx == 0 && r < M) part[(size_t)blockIdx.y * Mcap + r] = make_float4(m[u], ps[u], as[u], 0.f);
   }
 }
 
 __global__ void __launch_bounds__(1024, 1)
-supcon_mean_kernel(const float4* __restrict__ stats, const int32_t* __restrict__ M_dev, int Mcap,
-                   float* __restrict__ loss_out) {
+supcon_mean_kernel(float4* __restrict__ stats, const float4* __restrict__ parts, const float* __restrict__ row_w,
+                   const int32_t* __restrict__ M_dev, int Mcap, float* __restrict__ loss_out) {
   __shared__ float s_v[32];
   const int M = min(*M_dev, Mcap);
   float part = 0.f;
-  for (int r = threadIdx.x; r < M; r += blockDim.x) part += stats[r].w;
+  for (int r = threadIdx.x; r < M; r += blockDim.x) {
+    float m = -INFINITY, p = 0.f, a = 0.f;
+    for (int sidx = 0; sidx < kSplit; ++sidx) {              // fixed order: deterministic
+      const float4 q = parts[(size_t)sidx * Mcap + r];
+      if (q.x != -INFINITY) merge_stats(m, p, a, q.x, q.y, q.z);
+    }
+    const float lr = -logf(p / a) * __ldg(row_w + r);        // sim_loss.py:76-78
+    stats[r] = make_float4(m, p, a, lr);
+    part += lr;
+  }
   part = odw_warp_sum(part);
   if ((threadIdx.x & 31) == 0) s_v[threadIdx.x >> 5] = part;
   __syncthreads();
@@ -172,6 +182,9 @@ supcon_bwd_kernel(const float* __restrict__ F, const float* __restrict__ E, int 
   const int M = min(*M_dev, Mcap);
   const int r0 = blockIdx.x * kT;
   if (r0 >= M) return;
+  const int per_split = ((M + kT - 1) / kT + kSplit - 1) / kSplit * kT;
+  const int c_begin = blockIdx.y * per_split, c_end = min(M, c_begin + per_split);
+  if (c_begin >= c_end) return;
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
   const float gM = __ldg(gscale_dev) / (float)M;
   load_tile_kmajor(sA, F, E, R, row_src, r0, M);
@@ -192,7 +205,7 @@ supcon_bwd_kernel(const float* __restrict__ F, const float* __restrict__ E, int 
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc2[u][e] = 0.f;
 
-  for (int c0 = 0; c0 < M; c0 += kT) {
+  for (int c0 = c_begin; c0 < c_end; c0 += kT) {
     __syncthreads();
     load_tile_kmajor(sB, F, E, R, row_src, c0, M);
     if (threadIdx.x < kT) {
@@ -261,10 +274,11 @@ ODW_API int odwscl_supcon_fwd_f32(const float* F, const float* E, int R, const i
   if (!F || !row_src || !row_lab || !row_w || !M_dev || !stats) return ODWSCL_EINVAL;
   const int smem = 2 * kD * kLd * (int)sizeof(float);
   ODW_CUDA(cudaFuncSetAttribute(supcon_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  supcon_fwd_kernel<<<odw_cdiv(Mcap, kT), kThreads, smem, st>>>(F, E, R, row_src, row_lab, row_w, M_dev, Mcap,
-                                                                inv_temp, reinterpret_cast<float4*>(stats));
+  float4* parts = reinterpret_cast<float4*>(stats) + Mcap;              // [kSplit][Mcap] behind the merged rows
+  supcon_fwd_kernel<<<dim3(odw_cdiv(Mcap, kT), kSplit), kThreads, smem, st>>>(F, E, R, row_src, row_lab, row_w, M_dev,
+                                                                             Mcap, inv_temp, parts);
   ODW_LAUNCH_CHECK();
-  supcon_mean_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<const float4*>(stats), M_dev, Mcap, loss_out);
+  supcon_mean_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<float4*>(stats), parts, row_w, M_dev, Mcap, loss_out);
   ODW_LAUNCH_CHECK();
   return 0;
 }
@@ -278,7 +292,7 @@ ODW_API int odwscl_supcon_bwd_f32(const float* F, const float* E, int R, const i
   if (!F || !row_src || !row_lab || !row_w || !M_dev || !stats || !gscale_dev || !dF) return ODWSCL_EINVAL;
   const int smem = (2 * kD * kLd + kT * (kT + 1)) * (int)sizeof(float);
   ODW_CUDA(cudaFuncSetAttribute(supcon_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  supcon_bwd_kernel<<<odw_cdiv(Mcap, kT), kThreads, smem, (cudaStream_t)stream>>>(
+  supcon_bwd_kernel<<<dim3(odw_cdiv(Mcap, kT), kSplit), kThreads, smem, (cudaStream_t)stream>>>(
       F, E, R, row_src, row_lab, row_w, M_dev, Mcap, inv_temp, reinterpret_cast<const float4*>(stats), gscale_dev,
       dF, dE);
   ODW_LAUNCH_CHECK();
