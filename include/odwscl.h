@@ -161,6 +161,19 @@ int odwscl_od_layer_f32(const float* boxes, const int32_t* img_off, int B, int R
                         const int32_t* inst_cnt, float fg_thr, int64_t* labels, float* weights,
                         float* targets, odwscl_stream_t stream);
 
+/* ---- A6 (elementwise part): nn.ReLU(True) + nn.Dropout(p) of the fc6 / fc7 outputs (modeling/backbone/vgg16.py:
+ * 122-130) as ONE in-place pass: x <- relu(x) * keep / (1-p), keep ~ Bernoulli(1-p) from Philox4x32-10(seed, index/4).
+ * n % 4 == 0.  The backward needs no mask: gx = gy / (1-p) where the saved output y > 0, else 0. */
+int odwscl_relu_dropout_fwd_f32(float* x, long long n, float p, unsigned long long seed, odwscl_stream_t stream);
+int odwscl_relu_dropout_bwd_f32(const float* y, const float* gy, float* gx, long long n, float p,
+                                odwscl_stream_t stream);
+
+/* ---- A1 (operand layouts): the reference's [Cout,Cin,3,3] weights -> [Cout,3,3,Cin] (fprop operand, w_krsc) and the
+ * tap-flipped [Cin,3,3,Cout] (dgrad operand, w_crsk_flip) in one pass, optionally TF32-rounded (cvt.rna).  Either
+ * output may be null. */
+int odwscl_conv_weight_xform_f32(const float* w_oihw, int Cout, int Cin, float* w_krsc, float* w_crsk_flip,
+                                 int round_tf32, odwscl_stream_t stream);
+
 /* ---- A15: DropBlock2D apply (modeling/dropblock/drop_block.py:29-66) with a device-sampled
  * centre mask [R,ph,pw] (1.0 = drop centre): block mask by block x block dilation, global
  * renormalisation numel/sum, y = x * mask * scale in ONE pass over x [R,C,ph,pw].

@@ -28,6 +28,7 @@ _LAUNCHES = {
     "odwscl_dropblock_f32": 3, "odwscl_dropblock_rows_f32": 3, "odwscl_sim_nxn_f32": 2, "odwscl_gemm_nt_tf32": 1,
     "odwscl_conv3x3_nhwc_tf32": 1, "odwscl_conv3x3_wgrad_nhwc_tf32": 2, "odwscl_conv3x3_c3_f32": 1, "odwscl_maxpool2x2_nhwc_f32": 1,
     "odwscl_maxpool2x2_nhwc_bwd_f32": 1, "odwscl_split_tf32": 1,
+    "odwscl_relu_dropout_fwd_f32": 1, "odwscl_relu_dropout_bwd_f32": 1, "odwscl_conv_weight_xform_f32": 1,
 }
 
 _P, _I, _F, _Z = c_void_p, c_int, c_float, c_size_t
@@ -60,6 +61,9 @@ _SIGS = {
     "odwscl_maxpool2x2_nhwc_f32": (_I, [_P, _I, _I, _I, _I, _P, _P]),
     "odwscl_maxpool2x2_nhwc_bwd_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "odwscl_split_tf32": (_I, [_P, ctypes.c_longlong, _P, _P, _P]),
+    "odwscl_relu_dropout_fwd_f32": (_I, [_P, ctypes.c_longlong, _F, ctypes.c_ulonglong, _P]),
+    "odwscl_relu_dropout_bwd_f32": (_I, [_P, _P, _P, ctypes.c_longlong, _F, _P]),
+    "odwscl_conv_weight_xform_f32": (_I, [_P, _I, _I, _P, _P, _I, _P]),
     "odwscl_version": (_I, []),
     "odwscl_strerror": (ctypes.c_char_p, [_I]),
 }
@@ -397,6 +401,33 @@ def split_tf32(x):
     with torch.cuda.device(x.device):
         _call("odwscl_split_tf32", _ptr(x), x.numel(), _ptr(hi), _ptr(lo), _stream())
     return hi, lo
+
+
+def conv_weight_xform(w_oihw, want_fwd=True, want_dgrad=False, round_tf32=True):
+    """[Cout,Cin,3,3] -> ([Cout,3,3,Cin] or None, tap-flipped [Cin,3,3,Cout] or None), TF32-rounded, one pass."""
+    w_oihw = _chk(w_oihw, torch.float32, "w")
+    Cout, Cin = w_oihw.shape[:2]
+    wk = torch.empty((Cout, 3, 3, Cin), dtype=torch.float32, device=w_oihw.device) if want_fwd else None
+    wd = torch.empty((Cin, 3, 3, Cout), dtype=torch.float32, device=w_oihw.device) if want_dgrad else None
+    with torch.cuda.device(w_oihw.device):
+        _call("odwscl_conv_weight_xform_f32", _ptr(w_oihw), Cout, Cin, _ptr(wk), _ptr(wd), int(round_tf32), _stream())
+    return wk, wd
+
+
+def relu_dropout_(x, p, seed):
+    """in place: x <- relu(x) * Bernoulli(1-p) / (1-p)"""
+    assert x.is_contiguous() and x.dtype == torch.float32 and x.numel() % 4 == 0
+    with torch.cuda.device(x.device):
+        _call("odwscl_relu_dropout_fwd_f32", _ptr(x), x.numel(), float(p), ctypes.c_ulonglong(seed & (2 ** 64 - 1)), _stream())
+    return x
+
+
+def relu_dropout_backward(y, gy, p):
+    y, gy = _chk(y, torch.float32, "y"), _chk(gy, torch.float32, "gy")
+    gx = torch.empty_like(gy)
+    with torch.cuda.device(y.device):
+        _call("odwscl_relu_dropout_bwd_f32", _ptr(y), _ptr(gy), _ptr(gx), y.numel(), float(p), _stream())
+    return gx
 
 
 # ---------------------------------------------------------------- object discovery / SupCon

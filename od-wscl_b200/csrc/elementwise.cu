@@ -1,0 +1,121 @@
+// elementwise.cu -- small fused passes around the GEMM / conv kernels of the path.
+//
+//   relu_dropout       ReLU + Dropout(p) of the fc6 / fc7 outputs (modeling/backbone/vgg16.py:122-130: nn.ReLU(True),
+//                      nn.Dropout()) as ONE in-place pass with a counter-based RNG (Philox4x32-10): no mask tensor.  The
+//                      backward needs no mask either: y > 0 exactly where the unit was positive AND kept, so
+//                      gx = gy * scale * [y > 0] (one pass over gy and the saved activation).
+//   conv_weight_xform  [Cout,Cin,3,3] (the reference's state-dict layout) -> the two operand layouts the tcgen05 conv
+//                      kernels read, TF32-rounded, in one pass: [Cout,3,3,Cin] for fprop and the tap-flipped
+//                      [Cin,3,3,Cout] for dgrad.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+  const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+// 4 x 32 random bits for (seed, counter)
+__device__ __forceinline__ void philox4x32_10(unsigned long long seed, unsigned long long ctr, uint32_t (&out)[4]) {
+  uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u};
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+}
+
+__global__ void __launch_bounds__(256)
+relu_dropout_fwd_kernel(float4* __restrict__ x, long long n4, float p, float scale, unsigned long long seed) {
+  // keep iff u >= p with u uniform on [0,1) from 24 random bits (torch's bernoulli(1 - p) convention)
+  const uint32_t thr = (uint32_t)(p * 16777216.0f);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    uint32_t r[4];
+    philox4x32_10(seed, (unsigned long long)i, r);
+    float4 v = x[i];
+    v.x = (v.x > 0.f && (r[0] >> 8) >= thr) ? v.x * scale : 0.f;
+    v.y = (v.y > 0.f && (r[1] >> 8) >= thr) ? v.y * scale : 0.f;
+    v.z = (v.z > 0.f && (r[2] >> 8) >= thr) ? v.z * scale : 0.f;
+    v.w = (v.w > 0.f && (r[3] >> 8) >= thr) ? v.w * scale : 0.f;
+    x[i] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+relu_dropout_bwd_kernel(const float4* __restrict__ y, const float4* __restrict__ gy, float4* __restrict__ gx, long long n4,
+                        float scale) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 a = __ldcs(y + i), g = __ldcs(gy + i);
+    float4 o;
+    o.x = a.x > 0.f ? g.x * scale : 0.f;
+    o.y = a.y > 0.f ? g.y * scale : 0.f;
+    o.z = a.z > 0.f ? g.z * scale : 0.f;
+    o.w = a.w > 0.f ? g.w * scale : 0.f;
+    gx[i] = o;
+  }
+}
+
+__device__ __forceinline__ float rna_tf32_ew(float v) {
+  uint32_t b;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(v));
+  return __uint_as_float(b);
+}
+
+// one thread per (co, ci): reads the 9 taps (36 contiguous bytes), scatters them into both layouts
+__global__ void __launch_bounds__(256)
+conv_weight_xform_kernel(const float* __restrict__ w, int Cout, int Cin, float* __restrict__ w_krsc,
+                         float* __restrict__ w_crsk_flip, int round_tf32) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)Cout * Cin) return;
+  const int ci = (int)(idx % Cin), co = (int)(idx / Cin);
+  const float* src = w + idx * 9;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    float v = __ldg(src + t);
+    if (round_tf32) v = rna_tf32_ew(v);
+    if (w_krsc) w_krsc[((size_t)co * 9 + t) * Cin + ci] = v;                      // [Cout][r][s][Cin]
+    if (w_crsk_flip) w_crsk_flip[((size_t)ci * 9 + (8 - t)) * Cout + co] = v;     // [Cin][2-r][2-s][Cout]
+  }
+}
+
+}  // namespace
+
+ODW_API int odwscl_relu_dropout_fwd_f32(float* x, long long n, float p, unsigned long long seed, odwscl_stream_t stream) {
+  if (n < 0 || (n & 3) || p < 0.f || p >= 1.f) return ODWSCL_EINVAL;
+  if (n == 0) return 0;
+  if (!x) return ODWSCL_EINVAL;
+  const long long n4 = n / 4;
+  const int blocks = (int)min((long long)ODW_NUM_SMS * 8, (n4 + 255) / 256);
+  relu_dropout_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float4*>(x), n4, p, 1.f / (1.f - p), seed);
+  ODW_LAUNCH_CHECK();
+  return 0;
+}
+
+ODW_API int odwscl_relu_dropout_bwd_f32(const float* y, const float* gy, float* gx, long long n, float p,
+                                        odwscl_stream_t stream) {
+  if (n < 0 || (n & 3) || p < 0.f || p >= 1.f) return ODWSCL_EINVAL;
+  if (n == 0) return 0;
+  if (!y || !gy || !gx) return ODWSCL_EINVAL;
+  const long long n4 = n / 4;
+  const int blocks = (int)min((long long)ODW_NUM_SMS * 8, (n4 + 255) / 256);
+  relu_dropout_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(y),
+                                                                    reinterpret_cast<const float4*>(gy),
+                                                                    reinterpret_cast<float4*>(gx), n4, 1.f / (1.f - p));
+  ODW_LAUNCH_CHECK();
+  return 0;
+}
+
+ODW_API int odwscl_conv_weight_xform_f32(const float* w_oihw, int Cout, int Cin, float* w_krsc, float* w_crsk_flip,
+                                         int round_tf32, odwscl_stream_t stream) {
+  if (Cout <= 0 || Cin <= 0) return ODWSCL_EINVAL;
+  if (!w_oihw || (!w_krsc && !w_crsk_flip)) return ODWSCL_EINVAL;
+  const long long total = (long long)Cout * Cin;
+  conv_weight_xform_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, Cout, Cin, w_krsc,
+                                                                                         w_crsk_flip, round_tf32);
+  ODW_LAUNCH_CHECK();
+  return 0;
+}

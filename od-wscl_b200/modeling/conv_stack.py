@@ -28,12 +28,13 @@ LAYERS = [(64, 1, True, False), (64, 1, True, True), (128, 1, True, False), (128
           (512, 2, True, False), (512, 2, True, False), (512, 2, False, False)]
 
 
-def _conv(x, wk, bias, dil, flags, strict, mask_src=None, feeds_conv=True):
+def _conv(x, wk, bias, dil, flags, strict, mask_src=None, feeds_conv=True, w_rounded=False):
     """One convolution.  Single-pass mode: `x` is already TF32-rounded by its producer, the weights are rounded
-    here, and the output is rounded in the epilogue when another convolution consumes it (the tensor core
-    truncates fp32 operands; rounding first is what cuDNN's TF32 kernels do on load)."""
+    here (or by conv_weight_xform: w_rounded), and the output is rounded in the epilogue when another convolution
+    consumes it (the tensor core truncates fp32 operands; rounding first is what cuDNN's TF32 kernels do on load)."""
     if not strict:
-        capi.round_tf32_(wk)
+        if not w_rounded:
+            capi.round_tf32_(wk)
         return capi.conv3x3_nhwc(x, wk, bias, dilation=dil, flags=flags | (capi.CONV_ROUND if feeds_conv else 0),
                                  mask_src=mask_src)
     xh, xl = capi.split_tf32(x)
@@ -78,6 +79,7 @@ class _VGGStackFn(Function):
         needs_w = [ctx.needs_input_grad[2 + 2 * i] or ctx.needs_input_grad[3 + 2 * i] for i in range(n)]
         first_train = min([i for i in range(n) if needs_w[i]], default=n)
         saved = {}                  # tensors the backward needs, by name
+        wd_ops = {}                 # dgrad weight operands prepared in the forward (single-pass mode)
         a = capi.conv3x3_c3(x, ws[0], bs[0], relu=LAYERS[0][2], round_tf32=not strict)
         if first_train == 0:
             saved["x"] = x
@@ -92,8 +94,13 @@ class _VGGStackFn(Function):
                 break
             if i >= first_train:
                 saved["in%d" % i] = a                   # input of trainable layer i (wgrad; mask of layer i-1)
-            wk = ws[i].permute(0, 2, 3, 1).contiguous()
-            a = _conv(a, wk, bs[i], LAYERS[i][1], capi.CONV_RELU if LAYERS[i][2] else 0, strict, feeds_conv=i < n - 1)
+            if strict:
+                wk = ws[i].permute(0, 2, 3, 1).contiguous()
+            else:       # both operand layouts (fprop now, tap-flipped dgrad later) TF32-rounded in one pass over W
+                wk, wd_ops[i] = capi.conv_weight_xform(ws[i], want_fwd=True, want_dgrad=i > first_train)
+            a = _conv(a, wk, bs[i], LAYERS[i][1], capi.CONV_RELU if LAYERS[i][2] else 0, strict, feeds_conv=i < n - 1,
+                      w_rounded=not strict)
+        ctx.wd_ops = wd_ops
         ctx.strict, ctx.first_train, ctx.needs_w = strict, first_train, needs_w
         ctx.names = list(saved)
         ctx.save_for_backward(*saved.values(), *[ws[i] for i in range(n)])
@@ -137,15 +144,18 @@ class _VGGStackFn(Function):
                 break
             # DGRAD: d(input of layer i).  The input is either layer i-1's post-ReLU output (mask fused in the
             # epilogue) or its max-pooled version (mask fused into the pool backward).
-            wd = ws[i].flip(2, 3).permute(1, 2, 3, 0).contiguous()          # [Cin,3,3,Cout], taps flipped
+            wd = ctx.wd_ops.get(i)
+            pre = wd is not None
+            if not pre:
+                wd = ws[i].flip(2, 3).permute(1, 2, 3, 0).contiguous()      # [Cin,3,3,Cout], taps flipped
             prev_pool = LAYERS[i - 1][3]
             if prev_pool:
-                dp = _conv(dz, wd, None, dil, 0, ctx.strict)
+                dp = _conv(dz, wd, None, dil, 0, ctx.strict, w_rounded=pre)
                 dz = capi.maxpool2x2_nhwc_bwd(saved["a%d" % (i - 1)], dp, relu_mask=LAYERS[i - 1][2])
             elif LAYERS[i - 1][2]:
-                dz = _conv(dz, wd, None, dil, capi.CONV_MASK, ctx.strict, mask_src=xin)
+                dz = _conv(dz, wd, None, dil, capi.CONV_MASK, ctx.strict, mask_src=xin, w_rounded=pre)
             else:
-                dz = _conv(dz, wd, None, dil, 0, ctx.strict)
+                dz = _conv(dz, wd, None, dil, 0, ctx.strict, w_rounded=pre)
         if side is not None:
             main.wait_stream(side)                      # gradients are consumed (DDP hooks, optimizer) on the main stream
         return (None, None) + tuple(grads)

@@ -78,7 +78,10 @@ class RoIRegLossComputation(object):
         dev = class_score.device
         same = all(s == sizes[0] for s in sizes)
         if same:
-            final_det = F.softmax(det_score.view(B, sizes[0], C), dim=1).view(R, C)      # loss.py:237-244
+            # loss.py:237-244: softmax over the proposals of each image.  Done along a contiguous last axis
+            # ([B,C,N]): torch's strided-dim softmax kernel takes 60 + 77 us (fwd + bwd) on this 84 k-element tensor
+            final_det = F.softmax(det_score.view(B, sizes[0], C).transpose(1, 2).contiguous(), dim=2) \
+                .transpose(1, 2).reshape(R, C)
         else:
             final_det = torch.cat([F.softmax(d, dim=0) for d in det_score.split(sizes)], dim=0)
         final_score = class_score * final_det                                             # loss.py:246
@@ -219,15 +222,24 @@ class RoIRegLossComputation(object):
             sl1 = smooth_l1_loss(ref_bbox_preds[i].gather(1, map_inds), rt[i], beta=1, reduction=False)
             losses["loss_ref_reg%d" % i] = lmda * per_image_mean_sum((sl1 * (lw[i] * fg)[:, None]).sum(1))
 
-        with torch.no_grad():               # compute_avg_img_accuracy (loss.py:25-34) without .item()
-            for b in range(B):
-                k = max(len(pos[b]), 1)
-                lab_b = img_labels_d[b]
-                sl = slice(offs[b], offs[b + 1])
-                accs["acc_img"] = accs["acc_img"] + lab_b[img_score[b].topk(k)[1]].mean()
-                for i in range(3):
-                    rs = ref_scores[i][sl].sum(0)
-                    accs["acc_ref%d" % i] = accs["acc_ref%d" % i] + lab_b[1:][rs[1:].topk(k)[1]].mean()
+        with torch.no_grad():               # compute_avg_img_accuracy (loss.py:25-34) without .item(), batched over
+            # images: top-kmax once, positions past each image's own k masked out (same indices as per-image topk(k))
+            ks = [max(len(pos[b]), 1) for b in range(B)]
+            kmax = max(ks)
+            k_d = torch.tensor(ks, dtype=torch.float32).pin_memory().to(dev, non_blocking=True)
+            keep = (torch.arange(kmax, device=dev)[None] < k_d[:, None]).float()          # [B,kmax]
+
+            def topk_label_mean(score, labels):            # sum_b mean(labels[b][topk_k_b(score[b])])
+                idx = score.topk(kmax, dim=1)[1]
+                return ((labels.gather(1, idx) * keep).sum(1) / k_d).sum()
+
+            accs["acc_img"] = accs["acc_img"] + topk_label_mean(img_score, img_labels_d)
+            for i in range(3):
+                if same:
+                    rs = ref_scores[i].view(B, sizes[0], C).sum(1)
+                else:
+                    rs = torch.stack([r.sum(0) for r in ref_scores[i].split(sizes)])
+                accs["acc_ref%d" % i] = accs["acc_ref%d" % i] + topk_label_mean(rs[:, 1:], img_labels_d[:, 1:])
 
         for k in losses:
             if "sim" in k:

@@ -12,6 +12,25 @@ from .dropblock import DropBlock2D
 from .poolers import Pooler
 
 
+class _ReluDropoutFn(torch.autograd.Function):
+    """nn.ReLU(True) + nn.Dropout(p) (vgg16.py:124-125,128-129) as one in-place pass (csrc/elementwise.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, p, seed):
+        from .. import capi
+        y = capi.relu_dropout_(x, p, seed)
+        ctx.mark_dirty(x)
+        ctx.save_for_backward(y)
+        ctx.p = p
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        from .. import capi
+        (y,) = ctx.saved_tensors
+        return capi.relu_dropout_backward(y, gy.contiguous(), ctx.p), None, None
+
+
 class Identity(nn.Module):
     def __init__(self, *args, **kwargs):
         super().__init__()
@@ -90,6 +109,7 @@ class VGG16FC67ROIFeatureExtractor(nn.Module):
             self.dropblock = DropBlock2D(block_size=3, drop_prob=0.3)
         self.sim_drop = DropBlock2D(block_size=1, drop_prob=0.3)
         self.noise_sampler = None      # test hook: callable(shape, device) -> N(0,1) tensor
+        self.fuse_relu_dropout = True  # train: ReLU + Dropout of fc6 / fc7 as one in-place kernel
         self.fuse_clean_aug = True     # train: ROIPool + DropBlock into one [2R,...] batch, fc6/fc7 once
         if init_weights:
             for m in self.modules():
@@ -97,9 +117,24 @@ class VGG16FC67ROIFeatureExtractor(nn.Module):
                     nn.init.normal_(m.weight, 0, 0.01)
                     nn.init.constant_(m.bias, 0)
 
+    def run_classifier(self, x):
+        """self.classifier(x) (vgg16.py:122-130).  In training on the GPU the two ReLU + Dropout pairs run as one fused
+        in-place kernel each; the Linear layers stay with cuBLAS.  Same parameters, same state-dict keys."""
+        c = self.classifier
+        if not (self.training and self.fuse_relu_dropout and x.is_cuda and x.dtype == torch.float32):
+            return c(x)
+        for lin, drop in ((c[1], c[3]), (c[4], c[6])):
+            x = torch.nn.functional.linear(x, lin.weight, lin.bias)
+            if x.numel() % 4 == 0 and x.numel() > 0:
+                seed = int(torch.randint(0, 2 ** 62, (1,)).item())       # CPU generator: no device sync
+                x = _ReluDropoutFn.apply(x, float(drop.p), seed)
+            else:
+                x = drop(torch.relu(x))
+        return x
+
     def forward(self, x, proposals):                     # vgg16.py:148-153
         pooled_feat = self.pooler(x, proposals)
-        x = self.classifier(pooled_feat.view(pooled_feat.shape[0], -1))
+        x = self.run_classifier(pooled_feat.view(pooled_feat.shape[0], -1))
         return x, pooled_feat
 
     def can_fuse_clean_aug(self):
@@ -124,7 +159,7 @@ class VGG16FC67ROIFeatureExtractor(nn.Module):
             centres = (torch.rand(R, ph, pw, device=rois.device) < gamma).float()
         stash = {}
         buf = pool_and_augment(x[0].float(), rois, (ph, pw), pool.spatial_scale, centres.contiguous(), db.block_size, stash)
-        feats = self.classifier(buf.view(2 * R, -1))
+        feats = self.run_classifier(buf.view(2 * R, -1))
         clean, aug = split_rows(feats, R)
         pooled = buf.detach()[:R]
         pooled._odw_gather = lambda rows: gather_rows(buf, rows, R, stash)
@@ -134,7 +169,7 @@ class VGG16FC67ROIFeatureExtractor(nn.Module):
         return self.pooler(x, proposals)
 
     def forward_neck(self, x):                           # vgg16.py:159-162
-        return self.classifier(x.view(x.shape[0], -1))
+        return self.run_classifier(x.view(x.shape[0], -1))
 
     def forward_dropblock(self, pooled_feats, proposals):  # vgg16.py:165-167
         return self.dropblock(pooled_feats)

@@ -284,3 +284,34 @@ def test_roi_pool_bwd_multi_source(capi, B, C, H, W, R, S):
     assert got is not None and torch.equal(got.contiguous(), exp)
     only1 = capi.roi_pool_backward_multi(g1, None, None, None, rois, arg, B, C, H, W)
     assert torch.equal(only1.contiguous(), capi.roi_pool_backward(g1, rois, arg, 7, 7, B, C, H, W))
+
+
+def test_relu_dropout_fused(capi):
+    """ReLU + Dropout(p) in one in-place pass: zero where x <= 0, kept units scaled by 1/(1-p), keep rate 1-p, different
+    masks for different seeds; backward = gy * scale on the surviving units (no mask tensor)."""
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(4096, 512, generator=g).cuda()
+    for p in (0.0, 0.5, 0.3):
+        y = capi.relu_dropout_(x.clone(), p, 1234)
+        pos = x > 0
+        assert float(y[~pos].abs().sum()) == 0.0
+        kept = y > 0
+        torch.testing.assert_close(y[kept], x[kept] * (1.0 / (1.0 - p)), rtol=1e-6, atol=0)
+        rate = float(kept.sum()) / float(pos.sum())
+        assert abs(rate - (1.0 - p)) < 5e-3, (p, rate)
+        gy = torch.randn(x.shape, generator=g).cuda()
+        gx = capi.relu_dropout_backward(y, gy, p)
+        torch.testing.assert_close(gx, torch.where(kept, gy * (1.0 / (1.0 - p)), torch.zeros_like(gy)), rtol=1e-6, atol=0)
+    y1, y2 = capi.relu_dropout_(x.clone(), 0.5, 1), capi.relu_dropout_(x.clone(), 0.5, 2)
+    assert not torch.equal(y1 > 0, y2 > 0)
+    assert torch.equal(capi.relu_dropout_(x.clone(), 0.5, 1), y1)          # same seed, same mask
+
+
+def test_conv_weight_xform(capi):
+    g = torch.Generator().manual_seed(5)
+    w = torch.randn(96, 64, 3, 3, generator=g).cuda()
+    wk, wd = capi.conv_weight_xform(w, want_fwd=True, want_dgrad=True, round_tf32=False)
+    assert torch.equal(wk, w.permute(0, 2, 3, 1).contiguous())
+    assert torch.equal(wd, w.flip(2, 3).permute(1, 2, 3, 0).contiguous())
+    wk_r, wd_r = capi.conv_weight_xform(w, want_fwd=True, want_dgrad=True, round_tf32=True)
+    assert torch.equal(wk_r, capi.round_tf32_(wk.clone())) and torch.equal(wd_r, capi.round_tf32_(wd.clone()))
