@@ -185,8 +185,9 @@ class RoIRegLossComputation(object):
         Epad = model_sim(feature_extractor.forward_neck(aug))     # [2Kc,128]
         j = torch.arange(2 * P * Ncap, device=dev)                # K <= P*Ncap always: every address the kernels form is in range
         jj = j - k64
-        idx = torch.where(j < k64, torch.where(j < kv, j, torch.zeros_like(j)),
-                          torch.where((jj < kv) & (j < 2 * k64), jj + Kc, torch.zeros_like(j)))
+        pad = j % (2 * Kc)                     # padding entries spread over rows: their (zero) gradients do not pile up on one
+        idx = torch.where(j < k64, torch.where(j < kv, j, pad),
+                          torch.where((jj < kv) & (j < 2 * k64), jj + Kc, pad))
         E = Epad.index_select(0, idx).contiguous()
         self.overflow = (k64 > Kc).float()
         self._record_k(kdev)
