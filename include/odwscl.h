@@ -61,10 +61,12 @@ int odwscl_roi_pool_fwd_nhwc_f32(const float* feat_nhwc, int B, int C, int H, in
 int odwscl_roi_pool_bwd_nhwc_f32(const float* grad_out, const int32_t* argmax, const float* rois, int R, int B,
                                  int C, int H, int W, float* grad_in_nhwc, odwscl_stream_t stream);
 /* A4 for a pooled tensor with several consumers (weak_head.py:107-120): up to two dense gradients [R,C,7,7] and
- * one sparse one (srows [S] int64 roi indices, sgrad [S,C,7,7]) are summed while they are scattered.  EINVAL when
- * H*W*4 B exceeds the shared-memory plane (caller sums and uses odwscl_roi_pool_bwd_nhwc_f32). */
-int odwscl_roi_pool_bwd_nhwc_multi_f32(const float* grad_out, const float* grad_out2, const int64_t* srows,
-                                       const float* sgrad, int S, const int32_t* argmax, const float* rois, int R,
+ * one sparse one (srows [S] int64 roi indices, sgrad [S,C,7,7]) are summed while they are scattered.  mask2 (optional,
+ * [R,49]) multiplies grad_out2 per (roi, bin): with the block mask x scale written by odwscl_dropblock_mask_f32 the
+ * DropBlock backward of the augmented consumer happens inside the scatter.  EINVAL when H*W*4 B exceeds the
+ * shared-memory plane (caller sums and uses odwscl_roi_pool_bwd_nhwc_f32). */
+int odwscl_roi_pool_bwd_nhwc_multi_f32(const float* grad_out, const float* grad_out2, const float* mask2,
+                                       const int64_t* srows, const float* sgrad, int S, const int32_t* argmax, const float* rois, int R,
                                        int B, int C, int H, int W, float* grad_in_nhwc, odwscl_stream_t stream);
 
 /* ---- A5: ROIAlign (legacy, non-aligned).  Replaces _C.roi_align_forward/backward
@@ -182,6 +184,9 @@ int odwscl_conv_weight_xform_f32(const float* w_oihw, int Cout, int Cin, float* 
 int odwscl_dropblock_f32(const float* x, const float* centres, int R, int C, int ph, int pw,
                          int block, float* y, float* scale_io, int reuse_scale,
                          odwscl_stream_t stream);
+/* mask_out [R,ph*pw] = block_mask * scale_io[1] (the per-(roi, bin) factor of the forward AND of the backward). */
+int odwscl_dropblock_mask_f32(const float* centres, int R, int ph, int pw, int block, const float* scale_io,
+                              float* mask_out, odwscl_stream_t stream);
 /* Same over a PADDED batch: only the first *n_valid_dev rows (a device-resident count, <= R) take part in the
  * renormalisation and are written; rows past it are zero-filled.  Lets the caller size the batch from an upper
  * bound without reading the count back (no host synchronisation in the contrastive branch, loss.py:299-310). */

@@ -25,7 +25,7 @@ _LAUNCHES = {
     "odwscl_roi_align_bwd_f32": 1, "odwscl_box_iou_f32": 1, "odwscl_nms_f32": 1, "odwscl_nms_legacy_f32": 1,
     "odwscl_discover_phase_a_f32": 2, "odwscl_discover_phase_b_f32": 2, "odwscl_bank_assemble": 1,
     "odwscl_supcon_fwd_f32": 2, "odwscl_supcon_bwd_f32": 1, "odwscl_od_layer_f32": 1,
-    "odwscl_dropblock_f32": 3, "odwscl_dropblock_rows_f32": 3, "odwscl_sim_nxn_f32": 2, "odwscl_gemm_nt_tf32": 1,
+    "odwscl_dropblock_f32": 3, "odwscl_dropblock_rows_f32": 3, "odwscl_dropblock_mask_f32": 1, "odwscl_sim_nxn_f32": 2, "odwscl_gemm_nt_tf32": 1,
     "odwscl_conv3x3_nhwc_tf32": 1, "odwscl_conv3x3_wgrad_nhwc_tf32": 2, "odwscl_conv3x3_c3_f32": 1, "odwscl_maxpool2x2_nhwc_f32": 1,
     "odwscl_maxpool2x2_nhwc_bwd_f32": 1, "odwscl_split_tf32": 1,
     "odwscl_relu_dropout_fwd_f32": 1, "odwscl_relu_dropout_bwd_f32": 1, "odwscl_conv_weight_xform_f32": 1,
@@ -38,7 +38,8 @@ _SIGS = {
     "odwscl_roi_pool_bwd_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "odwscl_roi_pool_fwd_nhwc_f32": (_I, [_P, _I, _I, _I, _I, _P, _I, _F, _P, _P, _P]),
     "odwscl_roi_pool_bwd_nhwc_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
-    "odwscl_roi_pool_bwd_nhwc_multi_f32": (_I, [_P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "odwscl_roi_pool_bwd_nhwc_multi_f32": (_I, [_P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "odwscl_dropblock_mask_f32": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
     "odwscl_roi_align_fwd_f32": (_I, [_P, _I, _I, _I, _I, _P, _I, _F, _I, _I, _I, _P, _P]),
     "odwscl_roi_align_bwd_f32": (_I, [_P, _P, _I, _F, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "odwscl_box_iou_f32": (_I, [_P, _I, _P, _I, _I, _P, _P]),
@@ -111,9 +112,9 @@ _WORK = {
     # (grad, argmax, rois, R, B, C, H, W, ...): grad_out + argmax reads, zero + write of the map
     "odwscl_roi_pool_bwd_nhwc_f32": lambda a: ("byte", 8.0 * a[3] * a[5] * 49 + 8.0 * a[4] * a[5] * a[6] * a[7]),
     "odwscl_roi_pool_bwd_f32": lambda a: ("byte", 8.0 * a[3] * a[5] * a[8] * a[9] + 8.0 * a[4] * a[5] * a[6] * a[7]),
-    # (g1, g2, srows, sgrad, S, argmax, rois, R, B, C, H, W, ...): same algorithmic figure as the single-source call
+    # (g1, g2, mask2, srows, sgrad, S, argmax, rois, R, B, C, H, W, ...): same algorithmic figure as the single-source call
     # (SURVEY 8d counts ONE gradient read; the second dense source replaces a separate accumulate pass)
-    "odwscl_roi_pool_bwd_nhwc_multi_f32": lambda a: ("byte", 8.0 * a[7] * a[9] * 49 + 8.0 * a[8] * a[9] * a[10] * a[11]),
+    "odwscl_roi_pool_bwd_nhwc_multi_f32": lambda a: ("byte", 8.0 * a[8] * a[10] * 49 + 8.0 * a[9] * a[10] * a[11] * a[12]),
     # (F, N, out, ...): N x N x 128 contraction
     "odwscl_sim_nxn_f32": lambda a: ("flop", 2.0 * a[1] * a[1] * 128),
     # (A, B, C, M, N, K, ...)
@@ -203,7 +204,17 @@ def roi_pool_backward(grad, rois, argmax, ph, pw, B, C, H, W, channels_last=Fals
     return gin
 
 
-def roi_pool_backward_multi(grad, grad2, srows, sgrad, rois, argmax, B, C, H, W):
+def dropblock_mask(centres, block, scale_io):
+    """[R,49] per-(roi, bin) factor block_mask * scale of a DropBlock whose scale_io is known."""
+    centres = _chk(centres, torch.float32, "centres")
+    R, ph, pw = centres.shape
+    out = torch.empty((R, ph * pw), dtype=torch.float32, device=centres.device)
+    with torch.cuda.device(centres.device):
+        _call("odwscl_dropblock_mask_f32", _ptr(centres), R, ph, pw, int(block), _ptr(scale_io), _ptr(out), _stream())
+    return out
+
+
+def roi_pool_backward_multi(grad, grad2, srows, sgrad, rois, argmax, B, C, H, W, mask2=None):
     """NHWC grad map of a pooled tensor with up to two dense consumers and one sparse (gathered-rows) consumer.
     Returns None when the map does not fit the plane-centric kernel (the caller sums the gradients itself)."""
     if H * W * 4 > 220 * 1024:
@@ -213,6 +224,9 @@ def roi_pool_backward_multi(grad, grad2, srows, sgrad, rois, argmax, B, C, H, W)
     if grad2 is not None:
         grad2 = _chk(grad2, torch.float32, "grad2")
         assert grad2.shape == grad.shape
+    if mask2 is not None:
+        mask2 = _chk(mask2, torch.float32, "mask2")
+        assert grad2 is not None and mask2.numel() == grad.shape[0] * 49
     S = 0
     if srows is not None and srows.numel() > 0:
         srows, sgrad = _chk(srows, torch.int64, "srows"), _chk(sgrad, torch.float32, "sgrad")
@@ -220,7 +234,7 @@ def roi_pool_backward_multi(grad, grad2, srows, sgrad, rois, argmax, B, C, H, W)
         assert sgrad.shape[0] == S and sgrad.numel() == S * C * 49
     gin = torch.empty((B, H, W, C), dtype=torch.float32, device=grad.device)
     with torch.cuda.device(grad.device):
-        _call("odwscl_roi_pool_bwd_nhwc_multi_f32", _ptr(grad), _ptr(grad2), _ptr(srows) if S else None,
+        _call("odwscl_roi_pool_bwd_nhwc_multi_f32", _ptr(grad), _ptr(grad2), _ptr(mask2), _ptr(srows) if S else None,
               _ptr(sgrad) if S else None, S, _ptr(argmax), _ptr(rois), rois.shape[0], B, C, H, W, _ptr(gin), _stream())
     return gin.permute(0, 3, 1, 2)
 

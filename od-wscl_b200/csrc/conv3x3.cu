@@ -1065,6 +1065,39 @@ __global__ void maxpool2x2_nhwc_bwd_kernel(const float* __restrict__ x, const fl
   }
 }
 
+// same routing, one thread per 2x2 window x 4 channels: every byte of x / gy is read once, gx written once
+// (H, W even, C % 4 == 0)
+__global__ void __launch_bounds__(256)
+maxpool2x2_nhwc_bwd_v4_kernel(const float4* __restrict__ x, const float4* __restrict__ gy, float4* __restrict__ gx,
+                              int B, int H, int W, int C4, int relu_mask) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)B * Ho * Wo * C4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4);
+    long long p = i / C4;
+    const int wo = (int)(p % Wo); p /= Wo;
+    const int ho = (int)(p % Ho);
+    const int b = (int)(p / Ho);
+    const size_t o00 = (((size_t)b * H + 2 * ho) * W + 2 * wo) * C4 + c;
+    const size_t o01 = o00 + C4, o10 = o00 + (size_t)W * C4, o11 = o10 + C4;
+    const float4 v0 = __ldcs(x + o00), v1 = __ldcs(x + o01), v2 = __ldcs(x + o10), v3 = __ldcs(x + o11);
+    const float4 g = __ldcs(gy + i);
+    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0, r3 = r0;
+#define ODW_POOL_ROUTE(f)                                              \
+    {                                                                  \
+      int am = 0; float m = v0.f;                                      \
+      if (v1.f > m) { m = v1.f; am = 1; }                              \
+      if (v2.f > m) { m = v2.f; am = 2; }                              \
+      if (v3.f > m) { m = v3.f; am = 3; }                              \
+      const float gg = (relu_mask && !(m > 0.f)) ? 0.f : g.f;          \
+      if (am == 0) r0.f = gg; else if (am == 1) r1.f = gg; else if (am == 2) r2.f = gg; else r3.f = gg; \
+    }
+    ODW_POOL_ROUTE(x) ODW_POOL_ROUTE(y) ODW_POOL_ROUTE(z) ODW_POOL_ROUTE(w)
+#undef ODW_POOL_ROUTE
+    gx[o00] = r0; gx[o01] = r1; gx[o10] = r2; gx[o11] = r3;
+  }
+}
+
 __global__ void split_tf32_kernel(const float* __restrict__ x, long long n, float* __restrict__ hi, float* __restrict__ lo) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float v = x[i];
@@ -1145,6 +1178,15 @@ ODW_API int odwscl_maxpool2x2_nhwc_bwd_f32(const float* x, const float* gy, int 
   const long long total = (long long)B * H * W * C;
   if (total == 0) return 0;
   if (!x || !gy || !gx) return ODWSCL_EINVAL;
+  if ((C & 3) == 0 && (H & 1) == 0 && (W & 1) == 0) {
+    const long long t4 = total / 16;
+    const int blocks4 = (int)min((long long)ODW_NUM_SMS * 16, (t4 + 255) / 256);
+    maxpool2x2_nhwc_bwd_v4_kernel<<<blocks4, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(gy), reinterpret_cast<float4*>(gx), B, H, W,
+        C / 4, relu_mask);
+    ODW_LAUNCH_CHECK();
+    return 0;
+  }
   const int blocks = (int)min((long long)ODW_NUM_SMS * 16, (total + 255) / 256);
   maxpool2x2_nhwc_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, gy, gx, B, H, W, C, relu_mask);
   ODW_LAUNCH_CHECK();

@@ -79,7 +79,30 @@ dropblock_apply_kernel(const float* __restrict__ x, const float* __restrict__ ce
   }
 }
 
+__global__ void dropblock_mask_kernel(const float* __restrict__ centres, int R, int ph, int pw, int block,
+                                      const float* __restrict__ scale_io, float* __restrict__ mask_out) {
+  const int cells = ph * pw;
+  const float scale = scale_io[1];
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < (long long)R * cells;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(t / cells), k = (int)(t % cells);
+    mask_out[t] = block_mask_at(centres + (size_t)r * cells, ph, pw, block, k / pw, k % pw) * scale;
+  }
+}
+
 }  // namespace
+
+ODW_API int odwscl_dropblock_mask_f32(const float* centres, int R, int ph, int pw, int block, const float* scale_io,
+                                      float* mask_out, odwscl_stream_t stream) {
+  if (R < 0 || ph <= 0 || pw <= 0 || block <= 0) return ODWSCL_EINVAL;
+  if (R == 0) return 0;
+  if (!centres || !scale_io || !mask_out) return ODWSCL_EINVAL;
+  const long long total = (long long)R * ph * pw;
+  dropblock_mask_kernel<<<(int)min((long long)ODW_NUM_SMS * 4, (total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      centres, R, ph, pw, block, scale_io, mask_out);
+  ODW_LAUNCH_CHECK();
+  return 0;
+}
 
 ODW_API int odwscl_dropblock_rows_f32(const float* x, const float* centres, int R, int C, int ph, int pw, int block,
                                       float* y, float* scale_io, int reuse_scale, const int32_t* n_valid_dev,

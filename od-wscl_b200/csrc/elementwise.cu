@@ -65,21 +65,32 @@ __device__ __forceinline__ float rna_tf32_ew(float v) {
   return __uint_as_float(b);
 }
 
-// one thread per (co, ci): reads the 9 taps (36 contiguous bytes), scatters them into both layouts
+// CTA = 32 output channels x 32 input channels x 9 taps, staged in shared memory: the [Cout,Cin,9] source is read in
+// contiguous 1152-byte rows, the fprop layout [co][tap][ci] is written with ci fastest and the dgrad layout
+// [ci][8-tap][co] with co fastest -- all three coalesced.
 __global__ void __launch_bounds__(256)
 conv_weight_xform_kernel(const float* __restrict__ w, int Cout, int Cin, float* __restrict__ w_krsc,
                          float* __restrict__ w_crsk_flip, int round_tf32) {
-  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (idx >= (long long)Cout * Cin) return;
-  const int ci = (int)(idx % Cin), co = (int)(idx / Cin);
-  const float* src = w + idx * 9;
-#pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    float v = __ldg(src + t);
-    if (round_tf32) v = rna_tf32_ew(v);
-    if (w_krsc) w_krsc[((size_t)co * 9 + t) * Cin + ci] = v;                      // [Cout][r][s][Cin]
-    if (w_crsk_flip) w_crsk_flip[((size_t)ci * 9 + (8 - t)) * Cout + co] = v;     // [Cin][2-r][2-s][Cout]
+  __shared__ float s[32][32 * 9 + 1];                       // [co][ci*9 + tap]
+  const int co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
+  for (int i = threadIdx.x; i < 32 * 288; i += blockDim.x) {
+    const int co = i / 288, k = i % 288;                    // k = ci*9 + tap, contiguous in the source
+    float v = 0.f;
+    if (co0 + co < Cout && ci0 + k / 9 < Cin) v = __ldg(w + ((size_t)(co0 + co) * Cin + ci0) * 9 + k);
+    s[co][k] = round_tf32 ? rna_tf32_ew(v) : v;
   }
+  __syncthreads();
+  if (w_krsc)
+    for (int i = threadIdx.x; i < 32 * 9 * 32; i += blockDim.x) {
+      const int ci = i % 32, t = (i / 32) % 9, co = i / 288;
+      if (co0 + co < Cout && ci0 + ci < Cin) w_krsc[((size_t)(co0 + co) * 9 + t) * Cin + ci0 + ci] = s[co][ci * 9 + t];
+    }
+  if (w_crsk_flip)
+    for (int i = threadIdx.x; i < 32 * 9 * 32; i += blockDim.x) {
+      const int co = i % 32, t = (i / 32) % 9, ci = i / 288;
+      if (co0 + co < Cout && ci0 + ci < Cin)
+        w_crsk_flip[((size_t)(ci0 + ci) * 9 + (8 - t)) * Cout + co0 + co] = s[co][ci * 9 + t];
+    }
 }
 
 }  // namespace
@@ -113,9 +124,8 @@ ODW_API int odwscl_conv_weight_xform_f32(const float* w_oihw, int Cout, int Cin,
                                          int round_tf32, odwscl_stream_t stream) {
   if (Cout <= 0 || Cin <= 0) return ODWSCL_EINVAL;
   if (!w_oihw || (!w_krsc && !w_crsk_flip)) return ODWSCL_EINVAL;
-  const long long total = (long long)Cout * Cin;
-  conv_weight_xform_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, Cout, Cin, w_krsc,
-                                                                                         w_crsk_flip, round_tf32);
+  dim3 grid(odw_cdiv(Cin, 32), odw_cdiv(Cout, 32));
+  conv_weight_xform_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w_oihw, Cout, Cin, w_krsc, w_crsk_flip, round_tf32);
   ODW_LAUNCH_CHECK();
   return 0;
 }

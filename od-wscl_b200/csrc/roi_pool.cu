@@ -216,7 +216,7 @@ constexpr int kBwdChunkRois = 512;
 template <int NCH, bool NHWC>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 roi_pool_bwd_plane_kernel(const float* __restrict__ grad_out, const float* __restrict__ grad_out2,
-                          const int64_t* __restrict__ srows, const float* __restrict__ sgrad, int S,
+                          const float* __restrict__ mask2, const int64_t* __restrict__ srows, const float* __restrict__ sgrad, int S,
                           const int32_t* __restrict__ argmax, const float* __restrict__ rois, int R, int C, int HW,
                           float* __restrict__ grad_in) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -248,7 +248,15 @@ roi_pool_bwd_plane_kernel(const float* __restrict__ grad_out, const float* __res
       const size_t off = ((size_t)s_list[rl] * C + (size_t)cg * NCH) * 49 + 4 * q;
       float4 g = __ldcs(reinterpret_cast<const float4*>(grad_out + off));
       if (grad_out2 != nullptr) {                  // second consumer of the pooled features: summed on the fly
-        const float4 g2 = __ldcs(reinterpret_cast<const float4*>(grad_out2 + off));
+        float4 g2 = __ldcs(reinterpret_cast<const float4*>(grad_out2 + off));
+        if (mask2 != nullptr) {                    // ... through a per-(roi, bin) multiplier (the DropBlock backward)
+          const float* mk = mask2 + (size_t)s_list[rl] * 49;
+          const int k0 = (4 * q) % 49;
+          g2.x *= __ldg(mk + k0);
+          g2.y *= __ldg(mk + (k0 + 1 < 49 ? k0 + 1 : k0 - 48));
+          g2.z *= __ldg(mk + (k0 + 2 < 49 ? k0 + 2 : k0 - 47));
+          g2.w *= __ldg(mk + (k0 + 3 < 49 ? k0 + 3 : k0 - 46));
+        }
         g.x += g2.x; g.y += g2.y; g.z += g2.z; g.w += g2.w;
       }
       const int4 a = __ldcs(reinterpret_cast<const int4*>(argmax + off));
@@ -278,7 +286,11 @@ roi_pool_bwd_plane_kernel(const float* __restrict__ grad_out, const float* __res
       const int rl = it / kRun, e = it - rl * kRun;
       const size_t off = ((size_t)s_list[rl] * C + (size_t)cg * NCH) * 49 + e;
       const int a = __ldcs(argmax + off);
-      if (a >= 0) atomicAdd(acc + a * NCH + e / 49, __ldcs(grad_out + off) + (grad_out2 ? __ldcs(grad_out2 + off) : 0.f));
+      if (a >= 0) {
+        float g2 = grad_out2 ? __ldcs(grad_out2 + off) : 0.f;
+        if (mask2 != nullptr) g2 *= __ldg(mask2 + (size_t)s_list[rl] * 49 + e % 49);
+        atomicAdd(acc + a * NCH + e / 49, __ldcs(grad_out + off) + g2);
+      }
     }
     for (int it = threadIdx.x; it < S * kRun; it += blockDim.x) {
       const int k = it / kRun, e = it - k * kRun;
@@ -313,6 +325,7 @@ roi_pool_bwd_plane_kernel(const float* __restrict__ grad_out, const float* __res
 
 struct BwdExtra {                 // optional extra consumers of the pooled features (all device pointers)
   const float* grad_out2;
+  const float* mask2;             // [R,49] multiplier applied to grad_out2 (block mask * scale of the DropBlock), or null
   const int64_t* srows;
   const float* sgrad;
   int S;
@@ -324,7 +337,7 @@ static int launch_bwd_plane(const float* grad_out, const int32_t* argmax, const 
   const int smem = HW * NCH * (int)sizeof(float);
   ODW_CUDA(cudaFuncSetAttribute(roi_pool_bwd_plane_kernel<NCH, NHWC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   dim3 grid(C / NCH, B, odw_cdiv(R, kBwdChunkRois));
-  roi_pool_bwd_plane_kernel<NCH, NHWC><<<grid, kBwdThreads, smem, st>>>(grad_out, ex.grad_out2, ex.srows, ex.sgrad, ex.S,
+  roi_pool_bwd_plane_kernel<NCH, NHWC><<<grid, kBwdThreads, smem, st>>>(grad_out, ex.grad_out2, ex.mask2, ex.srows, ex.sgrad, ex.S,
                                                                          argmax, rois, R, C, HW, grad_in);
   ODW_LAUNCH_CHECK();
   return 0;
@@ -333,7 +346,7 @@ static int launch_bwd_plane(const float* grad_out, const int32_t* argmax, const 
 // picks the widest channel group whose plane fits in shared memory; false = no plane-centric path (7x7 only)
 template <bool NHWC>
 static int bwd_plane_dispatch(const float* grad_out, const int32_t* argmax, const float* rois, int R, int B, int C,
-                              int HW, float* grad_in, cudaStream_t st, bool* done, BwdExtra ex = BwdExtra{nullptr, nullptr, nullptr, 0}) {
+                              int HW, float* grad_in, cudaStream_t st, bool* done, BwdExtra ex = BwdExtra{nullptr, nullptr, nullptr, nullptr, 0}) {
   const size_t kMaxSmem = 220 * 1024;
   *done = true;
   if (C % 4 == 0 && (size_t)HW * 16 <= kMaxSmem) return launch_bwd_plane<4, NHWC>(grad_out, argmax, rois, R, B, C, HW, grad_in, st, ex);
@@ -436,8 +449,8 @@ ODW_API int odwscl_roi_pool_bwd_nhwc_f32(const float* grad_out, const int32_t* a
 // scattered, instead of being materialised as one more [R,C,7,7] tensor per consumer.  grad_out2, and the sparse
 // (srows [S] int64, sgrad [S,C,7,7]) source, may be null / empty.  Returns ODWSCL_EINVAL when the map does not fit the
 // plane-centric kernel (the caller then sums the gradients itself and calls odwscl_roi_pool_bwd_nhwc_f32).
-ODW_API int odwscl_roi_pool_bwd_nhwc_multi_f32(const float* grad_out, const float* grad_out2, const int64_t* srows,
-                                               const float* sgrad, int S, const int32_t* argmax, const float* rois, int R,
+ODW_API int odwscl_roi_pool_bwd_nhwc_multi_f32(const float* grad_out, const float* grad_out2, const float* mask2,
+                                               const int64_t* srows, const float* sgrad, int S, const int32_t* argmax, const float* rois, int R,
                                                int B, int C, int H, int W, float* grad_in_nhwc, odwscl_stream_t stream) {
   if (B < 0 || C < 0 || H < 0 || W < 0 || R < 0 || S < 0) return ODWSCL_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
@@ -450,5 +463,5 @@ ODW_API int odwscl_roi_pool_bwd_nhwc_multi_f32(const float* grad_out, const floa
   if (!grad_out || !argmax || !rois || (S > 0 && (!srows || !sgrad))) return ODWSCL_EINVAL;
   bool done = false;
   return bwd_plane_dispatch<true>(grad_out, argmax, rois, R, B, C, H * W, grad_in_nhwc, st, &done,
-                                  BwdExtra{grad_out2, srows, sgrad, S});
+                                  BwdExtra{grad_out2, mask2, srows, sgrad, S});
 }

@@ -64,11 +64,14 @@ class _PoolAugFn(Function):
         R = ctx.R
         bs, ch, h, w = ctx.input_shape
         g = g.contiguous()
-        g_aug, _ = capi.dropblock(g[R:], centres, ctx.block, scale_io)            # DropBlock backward of the augmented half
         srows, sgrad = ctx.stash.pop("rows", None), ctx.stash.pop("grads", None)
-        gin = capi.roi_pool_backward_multi(g[:R], g_aug, srows, sgrad, rois, argmax, bs, ch, h, w) \
-            if ctx.channels_last and ctx.out_hw == (7, 7) else None
+        gin = None
+        if ctx.channels_last and ctx.out_hw == (7, 7):
+            # the DropBlock backward of the augmented half (g[R:] * block_mask * scale) happens inside the scatter
+            bmask = capi.dropblock_mask(centres, ctx.block, scale_io)
+            gin = capi.roi_pool_backward_multi(g[:R], g[R:], srows, sgrad, rois, argmax, bs, ch, h, w, mask2=bmask)
         if gin is None:                                                          # maps too large for the plane kernel
+            g_aug, _ = capi.dropblock(g[R:], centres, ctx.block, scale_io)
             tot = g[:R] + g_aug
             if srows is not None and srows.numel() > 0:
                 tot.index_add_(0, srows, sgrad)

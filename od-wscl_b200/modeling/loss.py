@@ -135,10 +135,15 @@ class RoIRegLossComputation(object):
         """Bound for the next speculative step from the K values read back so far (non-blocking)."""
         if self._k_event is not None and self._k_event.query():
             k = int(self._k_host[0])
-            cap = (int(k * self.k_margin) + 64 + 63) // 64 * 64
+            cap = self._cap_for(k)
             self._k_cap = cap if self._k_cap is None else max(self._k_cap, cap)
             self._k_event = None
         return self._k_cap
+
+    def _cap_for(self, k):
+        """Bound for a batch of k positives: margin, then a coarse grid so the padded shapes (GEMM heuristics, allocator
+        blocks) change rarely."""
+        return (int(k * self.k_margin) + 64 + 255) // 256 * 256
 
     def _record_k(self, kdev):
         if self._k_host is None:
@@ -152,7 +157,7 @@ class RoIRegLossComputation(object):
         offA_h = st.offA.cpu()                                   # the one host sync of the step
         K = int(offA_h[P]) if P > 0 else 0
         if self.speculative_k:
-            cap = (int(K * self.k_margin) + 64 + 63) // 64 * 64
+            cap = self._cap_for(K)
             self._k_cap = cap if self._k_cap is None else max(self._k_cap, cap)
             self.overflow = torch.zeros((1,), dtype=torch.float32, device=st.offA.device)
         rows = st.rowsA[:K].long()

@@ -284,6 +284,16 @@ def test_roi_pool_bwd_multi_source(capi, B, C, H, W, R, S):
     assert got is not None and torch.equal(got.contiguous(), exp)
     only1 = capi.roi_pool_backward_multi(g1, None, None, None, rois, arg, B, C, H, W)
     assert torch.equal(only1.contiguous(), capi.roi_pool_backward(g1, rois, arg, 7, 7, B, C, H, W))
+    # second source through a per-(roi, bin) multiplier (the fused DropBlock backward)
+    cen = (torch.rand(R, 7, 7, generator=g) < 0.05).float().cuda()
+    _, sc = capi.dropblock(g2, cen, 3)
+    sc[1] = 2.0                                                          # power of two: products stay exact
+    bm = capi.dropblock_mask(cen, 3, sc)
+    masked = capi.roi_pool_backward_multi(g1, g2, srows, sgrad, rois, arg, B, C, H, W, mask2=bm)
+    tot2 = g1 + g2 * bm.view(R, 1, 7, 7)
+    if S:
+        tot2.index_add_(0, srows, sgrad)
+    assert torch.equal(masked.contiguous(), capi.roi_pool_backward(tot2, rois, arg, 7, 7, B, C, H, W))
 
 
 def test_relu_dropout_fused(capi):
