@@ -1,0 +1,56 @@
+"""Golden vectors for the input side from the REFERENCE ITSELF: data/datasets/coco.py unique_boxes,
+BoxList.clip_to_image / resize / transpose, boxlist_ops.remove_small_boxes, transforms.Normalize, to_image_list.
+Run in the build container only:  python -m oracle.gen_golden_data   (TEST INFRASTRUCTURE ONLY)"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_shims              # noqa: E402
+
+
+def main():
+    ref_shims.install()
+    from wetectron.data.datasets.coco import unique_boxes
+    from wetectron.data.transforms.transforms import Normalize
+    from wetectron.structures.bounding_box import FLIP_LEFT_RIGHT, BoxList
+    from wetectron.structures.boxlist_ops import remove_small_boxes
+    from wetectron.structures.image_list import to_image_list
+    rs = np.random.RandomState(7)
+    W, H = 500, 375
+    n = 400
+    x1 = rs.uniform(-30, W, n); y1 = rs.uniform(-30, H, n)
+    raw = np.stack([x1, y1, x1 + rs.uniform(1, 300, n), y1 + rs.uniform(1, 250, n)], 1).round()
+    raw[50:80] = raw[10:40]                         # duplicates
+    raw[100:110, 2] = raw[100:110, 0] + 5           # small boxes
+    raw = raw.astype(np.float32)
+    keep = unique_boxes(raw)
+    rois = raw[keep, :]
+    bl = BoxList(torch.tensor(rois.astype(np.float64)), (W, H), mode="xyxy")
+    bl = bl.clip_to_image(remove_empty=True)
+    bl = remove_small_boxes(boxlist=bl, min_size=20)
+    out = {"raw": raw, "W": W, "H": H, "unique_keep": keep, "filtered": bl.bbox.numpy()}
+    for tag, size in (("eq", (1000, 750)), ("neq", (864, 600))):
+        out["resized_" + tag] = bl.resize(size).bbox.numpy()
+        out["size_" + tag] = np.array(size)
+    out["flipped"] = bl.transpose(FLIP_LEFT_RIGHT).bbox.numpy()
+    g = torch.Generator().manual_seed(3)
+    img = torch.rand(3, 37, 53, generator=g)
+    out["img"] = img.numpy()
+    out["normalized"] = Normalize(mean=[102.9801, 115.9465, 122.7717], std=[1.0, 1.0, 1.0], to_bgr255=True)(img)[0].numpy()
+    imgs = [torch.rand(3, h, w, generator=g) for h, w in ((37, 53), (64, 40), (50, 70))]
+    il = to_image_list(imgs, 32)
+    for i, im in enumerate(imgs):
+        out["il_in%d" % i] = im.numpy()
+    out["il_tensors"] = il.tensors.numpy()
+    out["il_sizes"] = np.array([list(s) for s in il.image_sizes])
+    path = os.path.join(ROOT, "tests", "golden", "data_side.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, {k: np.asarray(v).shape for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    main()
