@@ -194,6 +194,14 @@ int odwscl_dropblock_rows_f32(const float* x, const float* centres, int R, int C
                               int block, float* y, float* scale_io, int reuse_scale,
                               const int32_t* n_valid_dev, odwscl_stream_t stream);
 
+/* ---- N4 (test time): PostProcessor.filter_results (roi_heads/box_head/inference.py:216-258) -- for every foreground
+ * class j in [1,C): candidates with scores[i,j] > score_thr, torchvision-semantics NMS at `thr` on boxes[i, 4j..4j+3],
+ * all classes in ONE launch (one CTA per class, sort + sweep in shared memory, no host round trip).  boxes [N,C*4],
+ * scores [N,C]; keep [C,N] int32 (row j = kept proposal indices, descending score), n_keep [C] (n_keep[0] = 0).
+ * N <= 8192. */
+int odwscl_nms_per_class_f32(const float* boxes, const float* scores, int n, int C, float score_thr, float thr,
+                             int32_t* keep, int32_t* n_keep, odwscl_stream_t stream);
+
 /* ---- A11 (drop-in for loss.py:319): full N x N similarity F F^T on the tensor cores
  * (tcgen05.mma kind::tf32 fed by TMA, accumulators in TMEM; 3xTF32 operand split so the result is
  * fp32-accurate).  out [N,N] fp32; ws sized by odwscl_sim_nxn_ws_bytes(N). */

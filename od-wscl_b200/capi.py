@@ -45,6 +45,7 @@ _SIGS = {
     "odwscl_box_iou_f32": (_I, [_P, _I, _P, _I, _I, _P, _P]),
     "odwscl_nms_f32": (_I, [_P, _P, _I, _F, _P, _P, _P]),
     "odwscl_nms_legacy_f32": (_I, [_P, _P, _I, _F, _P, _P, _P]),
+    "odwscl_nms_per_class_f32": (_I, [_P, _P, _I, _I, _F, _F, _P, _P, _P]),
     "odwscl_discover_phase_a_f32": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _I, _F] + [_P] * 7 + [_P]),
     "odwscl_discover_phase_b_f32": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _I] + [_P] * 8 + [_F] + [_P] * 7 + [_P]),
     "odwscl_bank_assemble": (_I, [_P, _P, _I, _I, _I, _I, _I] + [_P] * 8 + [_I] + [_P] * 4 + [_P]),
@@ -289,6 +290,19 @@ def nms(boxes, scores, thr):
 def nms_legacy(boxes, scores, thr):
     keep, cnt = _nms("odwscl_nms_legacy_f32", boxes, scores, thr)
     return keep[: int(cnt.item())]
+
+
+def nms_per_class(boxes, scores, score_thr, nms_thr):
+    """boxes [N,C*4], scores [N,C] -> (keep [C,N] int32, n_keep [C] int32); all foreground classes in one launch."""
+    boxes, scores = _chk(boxes, torch.float32, "boxes"), _chk(scores, torch.float32, "scores")
+    N, C = scores.shape
+    assert boxes.shape == (N, C * 4)
+    keep = torch.empty((C, max(N, 1)), dtype=torch.int32, device=boxes.device)
+    cnt = torch.empty((C,), dtype=torch.int32, device=boxes.device)
+    with torch.cuda.device(boxes.device):
+        _call("odwscl_nms_per_class_f32", _ptr(boxes), _ptr(scores), N, C, float(score_thr), float(nms_thr), _ptr(keep),
+              _ptr(cnt), _stream())
+    return keep, cnt
 
 
 def sim_nxn(F):

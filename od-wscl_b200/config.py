@@ -44,7 +44,9 @@ _DEFAULTS = {
         "DEVICE": "cuda",
         "CLS_AGNOSTIC_BBOX_REG": False,
         "BACKBONE": {"CONV_BODY": "VGG16-OICR", "FREEZE_CONV_BODY_AT": 2},
-        "ROI_HEADS": {"FG_IOU_THRESHOLD": 0.5, "BBOX_REG_WEIGHTS": (10.0, 10.0, 5.0, 5.0)},
+        "ROI_HEADS": {"FG_IOU_THRESHOLD": 0.5, "BBOX_REG_WEIGHTS": (10.0, 10.0, 5.0, 5.0),
+                      # test time (configs/voc/voc07_contra_db_b8_lr0.01_mcg.yaml:8-10, config/defaults.py:233)
+                      "SCORE_THRESH": 0.0, "NMS": 0.4, "DETECTIONS_PER_IMG": 100},
         "ROI_BOX_HEAD": {"FEATURE_EXTRACTOR": "VGG16.roi_head", "POOLER_METHOD": "ROIPool",
                          "POOLER_RESOLUTION": 7, "POOLER_SCALES": (0.125,), "POOLER_SAMPLING_RATIO": 0,
                          "NUM_CLASSES": 21},
@@ -55,6 +57,8 @@ _DEFAULTS = {
     "SOLVER": {"CONTRA": True, "MAX_ITER": 30000, "BASE_LR": 0.01, "MOMENTUM": 0.9, "WEIGHT_DECAY": 0.0001,
                "BIAS_LR_FACTOR": 2, "WEIGHT_DECAY_BIAS": 0},
     "DB": {"METHOD": "dropblock"},
+    # the multi-scale TTA loop (engine/bbox_aug.py) is outside this package: a single-scale eval filters directly
+    "TEST": {"BBOX_AUG": {"ENABLED": False}},
     "DATALOADER": {"SIZE_DIVISIBILITY": 32},
     "nms": 0.1, "lmda": 0.03, "iou": 0.5, "temp": 0.2, "thres": 0.5, "loss": "supconv2", "pos_update": 0.0,
     "OUTPUT_DIR": ".",

@@ -56,6 +56,40 @@ nms_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores, i
   }
 }
 
+// Test-time filter (box_head/inference.py:216-258, filter_results): one CTA per foreground class j -- candidates with
+// scores[i,j] > score_thr (ascending i), sorted by score (desc, index asc on ties), greedy NMS at `thr` without the +1
+// (torchvision.ops.nms through boxlist_nms, structures/boxlist_ops.py:13-36).  boxes [N, C*4], scores [N, C];
+// keep [C, N] int32 (row j: kept proposal indices in descending-score order), n_keep [C] (row 0 = background = 0).
+__global__ void __launch_bounds__(odw::kCtaThreads, 1)
+nms_per_class_kernel(const float* __restrict__ boxes, const float* __restrict__ scores, int n, int C, int L,
+                     float score_thr, float thr, int32_t* __restrict__ keep, int32_t* __restrict__ n_keep) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  float4* s_box = reinterpret_cast<float4*>(smem);
+  float* s_key = reinterpret_cast<float*>(s_box + L);
+  int* s_id = reinterpret_cast<int*>(s_key + L);
+  int* s_scan = s_id + L;
+  unsigned char* s_sup = reinterpret_cast<unsigned char*>(s_scan + 64);
+  const int j = blockIdx.x + 1;
+  if (blockIdx.x == 0 && threadIdx.x == 0) n_keep[0] = 0;
+  const int nc = odw::cta_compact(
+      n, s_scan, [&](int i) { return __ldg(scores + (size_t)i * C + j) > score_thr; },
+      [&](int k, int i) { s_key[k] = __ldg(scores + (size_t)i * C + j); s_id[k] = i; });
+  int nk = 0;
+  if (nc > 0) {
+    const int L2 = odw::next_pow2(nc < 32 ? 32 : nc);
+    for (int t = nc + threadIdx.x; t < L2; t += blockDim.x) { s_key[t] = -INFINITY; s_id[t] = INT_MAX; }
+    for (int t = threadIdx.x; t < L2; t += blockDim.x) s_sup[t] = 0;
+    __syncthreads();
+    odw::cta_bitonic_sort(s_key, s_id, L2);
+    for (int t = threadIdx.x; t < nc; t += blockDim.x)
+      s_box[t] = __ldg(reinterpret_cast<const float4*>(boxes + ((size_t)s_id[t] * C + j) * 4));
+    __syncthreads();
+    int32_t* out = keep + (size_t)j * n;
+    nk = odw::cta_nms_sweep(s_box, s_sup, nc, thr, 0.f, [&](int k, int pos) { out[k] = s_id[pos]; });
+  }
+  if (threadIdx.x == 0) n_keep[j] = nk;
+}
+
 template <bool kLegacy>
 int launch_nms(const float* boxes, const float* scores, int n, float thr, int64_t* keep, int32_t* n_keep,
                odwscl_stream_t stream) {
@@ -101,4 +135,23 @@ ODW_API int odwscl_nms_f32(const float* boxes, const float* scores, int n, float
 ODW_API int odwscl_nms_legacy_f32(const float* boxes, const float* scores, int n, float thr, int64_t* keep,
                                   int32_t* n_keep, odwscl_stream_t stream) {
   return launch_nms<true>(boxes, scores, n, thr, keep, n_keep, stream);
+}
+
+ODW_API int odwscl_nms_per_class_f32(const float* boxes, const float* scores, int n, int C, float score_thr, float thr,
+                                     int32_t* keep, int32_t* n_keep, odwscl_stream_t stream) {
+  if (n < 0 || n > kNmsMax || C < 1) return ODWSCL_EINVAL;
+  if (!n_keep) return ODWSCL_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0 || C == 1) {
+    ODW_CUDA(cudaMemsetAsync(n_keep, 0, (size_t)C * sizeof(int32_t), st));
+    return 0;
+  }
+  if (!boxes || !scores || !keep) return ODWSCL_EINVAL;
+  int L = 32;
+  while (L < n) L <<= 1;
+  const size_t smem = (size_t)L * (16 + 4 + 4 + 1) + 64 * 4;
+  ODW_CUDA(cudaFuncSetAttribute(nms_per_class_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  nms_per_class_kernel<<<C - 1, odw::kCtaThreads, smem, st>>>(boxes, scores, n, C, L, score_thr, thr, keep, n_keep);
+  ODW_LAUNCH_CHECK();
+  return 0;
 }

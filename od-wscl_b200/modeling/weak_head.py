@@ -19,6 +19,11 @@ class ROIWeakRegHead(nn.Module):
         self.HEUR = cfg.MODEL.ROI_WEAK_HEAD.REGRESS_HEUR
         self.DB_METHOD = cfg.DB.METHOD
         self.model_sim = Sim_Net(cfg, self.feature_extractor.out_channels)
+        from .postprocess import PostProcessor
+        self.strong_post_processor = PostProcessor(                     # box_head/inference.py:260-283
+            score_thresh=cfg.MODEL.ROI_HEADS.SCORE_THRESH, nms=cfg.MODEL.ROI_HEADS.NMS,
+            detections_per_img=cfg.MODEL.ROI_HEADS.DETECTIONS_PER_IMG, weights=cfg.MODEL.ROI_HEADS.BBOX_REG_WEIGHTS,
+            cls_agnostic_bbox_reg=cfg.MODEL.CLS_AGNOSTIC_BBOX_REG, bbox_aug_enabled=cfg.TEST.BBOX_AUG.ENABLED)
 
     def go_through_cdb(self, features, proposals, model_cdb):              # weak_head.py:87-99
         if not self.training or self.DB_METHOD == "none":
@@ -41,10 +46,13 @@ class ROIWeakRegHead(nn.Module):
         clean_roi_feats, clean_pooled_feats = self.feature_extractor.forward(features, proposals)     # :107
         if not self.training:
             cls_score, det_score, ref_scores, ref_bbox_preds = self.predictor(clean_roi_feats, proposals)
-            # test-time post-processing (box_head/inference.py) is SURVEY row N4 ("next"): return raw scores
+            # testing_forward, HEUR "AVG" (weak_head.py:124-135): mean of the refinement heads, decode, per-class NMS
+            if self.HEUR != "AVG":
+                raise NotImplementedError("REGRESS_HEUR %r: every shipped config tests with 'AVG'" % self.HEUR)
             final_score = torch.mean(torch.stack(ref_scores), dim=0)
             final_regression = torch.mean(torch.stack(ref_bbox_preds), dim=0)
-            return clean_roi_feats, (final_score, final_regression), {}, {}
+            result = self.strong_post_processor((final_score, final_regression), proposals, softmax_on=False)
+            return clean_roi_feats, result, {}, {}
         sim_feature = self.model_sim(clean_roi_feats)                                                 # :110
         aug_pooled_feats = self.go_through_cdb(clean_pooled_feats, proposals, model_cdb)              # :111
         aug_roi_feats = self.feature_extractor.forward_neck(aug_pooled_feats)                         # :112

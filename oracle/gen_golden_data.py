@@ -52,5 +52,41 @@ def main():
     print("wrote", path, {k: np.asarray(v).shape for k, v in out.items()})
 
 
+
+
+def gen_postprocess():
+    """N4: PostProcessor.filter_results and BoxCoder.decode of the reference (CPU)."""
+    ref_shims.install()
+    from wetectron.modeling.box_coder import BoxCoder
+    from wetectron.modeling.roi_heads.box_head.inference import PostProcessor
+    g = torch.Generator().manual_seed(11)
+    out = {}
+    for tag, (N, C, W, H, cap) in {"a": (300, 21, 500, 375, 100), "b": (900, 21, 800, 600, 100), "c": (64, 81, 640, 480, 40)}.items():
+        x1 = torch.rand(N, generator=g) * (W - 60); y1 = torch.rand(N, generator=g) * (H - 60)
+        ref_boxes = torch.stack([x1, y1, x1 + 20 + torch.rand(N, generator=g) * (W - 21 - x1),
+                                 y1 + 20 + torch.rand(N, generator=g) * (H - 21 - y1)], 1).round()
+        reg = torch.randn(N, C * 4, generator=g) * 0.5
+        scores = torch.softmax(torch.randn(N, C, generator=g) * 2, 1)
+        scores[::7] = scores[3]                                   # exact score ties across proposals
+        coder = BoxCoder(weights=(10., 10., 5., 5.))
+        dec = coder.decode(reg, ref_boxes)
+        dec_saved = dec.clone()                                   # prepare_boxlist + clip_to_image clamp `dec` in place
+        pp = PostProcessor(score_thresh=0.0 if tag != "c" else 0.02, nms=0.4, detections_per_img=cap, box_coder=coder)
+        bl = pp.prepare_boxlist(dec, scores, (W, H)).clip_to_image(remove_empty=False)
+        clipped = bl.bbox.reshape(N, C * 4).clone()
+        res = pp.filter_results(bl, C)
+        out.update({tag + "_ref_boxes": ref_boxes.numpy(), tag + "_reg": reg.numpy(), tag + "_scores": scores.numpy(),
+                    tag + "_decoded": dec_saved.numpy(), tag + "_clipped": clipped.numpy(), tag + "_size": np.array([W, H]),
+                    tag + "_cap": cap, tag + "_thr": pp.score_thresh,
+                    tag + "_out_boxes": res.bbox.numpy(), tag + "_out_scores": res.get_field("scores").numpy(),
+                    tag + "_out_labels": res.get_field("labels").numpy()})
+    path = os.path.join(ROOT, "tests", "golden", "postprocess.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, {k: np.asarray(v).shape for k, v in out.items() if "out" in k})
+
+
 if __name__ == "__main__":
-    main()
+    if "--postprocess" in sys.argv:
+        gen_postprocess()
+    else:
+        main()
