@@ -319,22 +319,40 @@ static int launch_conv_2cta(const CUtensorMap& mx, const CUtensorMap& mw, const 
 }
 
 // ---------------------------------------------------------------------------------------------
-// PERSISTENT CTA-pair version with a stream-K schedule.  The one-tile-per-pair kernel above loses two things the
-// profile shows: the epilogue / pipeline fill of each tile is not overlapped with the next tile's MMAs (tensor pipe
-// 77 % busy while active), and 304 tiles on 148 SMs run as 3 waves instead of 2.05 (51 % busy over the elapsed time).
-// Here NP resident pairs split the linearised (pair-tile, k-iteration) space into NP equal contiguous ranges, so every
-// SM gets the same number of MMAs; a pair-tile that straddles two ranges is finished by the pair holding its HEAD
-// (k = 0 ..), which adds the TAIL partial the neighbouring pair left in a global workspace (that pair computed it as
-// its FIRST work item, long before).  Accumulators are double-buffered in TMEM (2 x 256 columns): the epilogue
-// warps drain tile i while the MMA thread is already accumulating tile i+1.
+// PERSISTENT CTA-pair version.  The one-tile-per-pair kernel above loses two things the profile shows: the epilogue /
+// pipeline fill of each tile is not overlapped with the next tile's MMAs, and 304 tiles on 148 SMs run as 3 waves
+// instead of 2.05.  Here NP resident pairs each take floor(T/NP) WHOLE pair-tiles, round by round and all at the same
+// k at the same time (so the 37+ pairs that need the same weight rows ask L2 for them together -- measured: 740 TF/s
+// when the tile count divides evenly vs 614 TF/s with skewed k ranges), and the T mod NP leftover tiles are split
+// along K over all the pairs (S = NP / leftover slices per tile).  The S partial accumulators of a leftover tile go
+// to a global workspace; the S CTAs then reduce 16-column chunks of it in a fixed order and run the fused epilogue
+// (all pairs are co-resident, so waiting on the arrival counter cannot deadlock).  Accumulators are double-buffered
+// in TMEM (2 x 256 columns): the epilogue warps drain tile i while the MMA thread already accumulates tile i+1.
 struct ConvSkParams {
-  int n_ptiles;        // pair-tiles = (pixel tiles / 2) * (Cout / 256)
+  int n_ptiles;        // T: pair-tiles = (pixel tiles / 2) * (Cout / 256)
   int n_ntiles;        // Cout / 256
   int kiters;          // 9 * Cin / 32
-  int per_pair;        // k-iterations per pair (ceil)
-  float* ws;           // [NP][2][128][256] partial accumulators
-  int* flags;          // [NP][2], zeroed before the launch
+  int np;              // resident pairs
+  int rounds;          // T / np whole tiles per pair
+  int left;            // T - rounds * np leftover tiles
+  int slices;          // K slices per leftover tile (np / left), 0 if none
+  float* ws;           // [left * slices][2][128][256] partial accumulators
+  int* flags;          // [left][2] arrival counters, zeroed before the launch
 };
+
+struct ConvSkItem { int tile, k0, k1, left_idx, slice; };   // left_idx < 0: a whole tile
+
+__device__ __forceinline__ bool conv_sk_item(const ConvSkParams& sk, int pair, int idx, ConvSkItem& it) {
+  if (idx < sk.rounds) { it.tile = idx * sk.np + pair; it.k0 = 0; it.k1 = sk.kiters; it.left_idx = -1; it.slice = 0; return true; }
+  if (idx == sk.rounds && sk.left > 0 && pair < sk.left * sk.slices) {
+    it.left_idx = pair / sk.slices; it.slice = pair - it.left_idx * sk.slices;
+    it.tile = sk.rounds * sk.np + it.left_idx;
+    it.k0 = (int)((long long)it.slice * sk.kiters / sk.slices);
+    it.k1 = (int)((long long)(it.slice + 1) * sk.kiters / sk.slices);
+    return true;
+  }
+  return false;
+}
 
 template <int STAGES>
 __global__ void __launch_bounds__(192, 1)
@@ -354,9 +372,6 @@ conv3x3_tf32_2cta_sk_kernel(const __grid_constant__ CUtensorMap map_x, const __g
   const int pair = blockIdx.x >> 1;
   const int TW = 1 << tw_log2, TH = kBM >> tw_log2;
   const int cchunks = Cin / tc::kTileK;
-  const long long total = (long long)sk.n_ptiles * sk.kiters;
-  const long long g_begin = (long long)pair * sk.per_pair;
-  const long long g_end = min(total, g_begin + sk.per_pair);
 
   if (warp == 0 && tc::elect_one()) {
     tc::tma_prefetch_desc(&map_x);
@@ -385,13 +400,12 @@ conv3x3_tf32_2cta_sk_kernel(const __grid_constant__ CUtensorMap map_x, const __g
   if (warp == 0) {
     if (tc::elect_one()) {
       int it = 0;
-      for (long long g = g_begin; g < g_end;) {
-        const int pt = (int)(g / sk.kiters), k0 = (int)(g - (long long)pt * sk.kiters);
-        const int k1 = (int)min((long long)sk.kiters, (long long)k0 + (g_end - g));
+      ConvSkItem wi;
+      for (int item = 0; conv_sk_item(sk, pair, item, wi); ++item) {
         int b, h0, w0, n0;
-        tile_coords(pt, b, h0, w0, n0);
-        int tap = k0 / cchunks, cc = k0 - tap * cchunks;
-        for (int kk = k0; kk < k1; ++kk, ++it) {
+        tile_coords(wi.tile, b, h0, w0, n0);
+        int tap = wi.k0 / cchunks, cc = wi.k0 - tap * cchunks;
+        for (int kk = wi.k0; kk < wi.k1; ++kk, ++it) {
           const int s = it % STAGES;
           tc::mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
           if (crank == 0) tc::mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
@@ -401,21 +415,19 @@ conv3x3_tf32_2cta_sk_kernel(const __grid_constant__ CUtensorMap map_x, const __g
           tc::tma_load_2d_2sm(a + A_BYTES, &map_w, &full_bar[s], tap * Cin + cc * tc::kTileK, n0 + (int)crank * (BN / 2));
           if (++cc == cchunks) { cc = 0; ++tap; }
         }
-        g += k1 - k0;
       }
     }
   } else if (warp == 1) {
     if (crank == 0 && tc::elect_one()) {
       constexpr uint32_t idesc = tc::umma_idesc_tf32(2 * kBM, BN);
-      int it = 0, item = 0;
-      for (long long g = g_begin; g < g_end; ++item) {
-        const int pt = (int)(g / sk.kiters), k0 = (int)(g - (long long)pt * sk.kiters);
-        const int k1 = (int)min((long long)sk.kiters, (long long)k0 + (g_end - g));
+      int it = 0;
+      ConvSkItem wi;
+      for (int item = 0; conv_sk_item(sk, pair, item, wi); ++item) {
         const int buf = item & 1;
         tc::mbar_wait(&tmem_empty_bar[buf], ((item >> 1) & 1) ^ 1);     // both CTAs drained this accumulator
         tc::tc_fence_after();
         const uint32_t acc = tmem_base + buf * BN;
-        for (int kk = k0; kk < k1; ++kk, ++it) {
+        for (int kk = wi.k0; kk < wi.k1; ++kk, ++it) {
           const int s = it % STAGES;
           tc::mbar_wait(&full_bar[s], (it / STAGES) & 1);
           tc::tc_fence_after();
@@ -423,60 +435,99 @@ conv3x3_tf32_2cta_sk_kernel(const __grid_constant__ CUtensorMap map_x, const __g
           const uint64_t ad = tc::umma_desc_sw128(a), bd = tc::umma_desc_sw128(a + A_BYTES);
 #pragma unroll
           for (int k = 0; k < tc::kTileK / tc::kUmmaK; ++k)
-            tc::umma_tf32_2sm(acc, ad + 2 * k, bd + 2 * k, idesc, (kk != k0) || (k != 0));
+            tc::umma_tf32_2sm(acc, ad + 2 * k, bd + 2 * k, idesc, (kk != wi.k0) || (k != 0));
           tc::umma_commit_2sm_mc(&empty_bar[s], 3);
         }
         tc::umma_commit_2sm_mc(&tmem_full_bar[buf], 3);
-        g += k1 - k0;
       }
     }
   } else {
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    int item = 0;
     float v[32];
-    for (long long g = g_begin; g < g_end; ++item) {
-      const int pt = (int)(g / sk.kiters), k0 = (int)(g - (long long)pt * sk.kiters);
-      const int k1 = (int)min((long long)sk.kiters, (long long)k0 + (g_end - g));
-      g += k1 - k0;
+    ConvSkItem wi;
+    for (int item = 0; conv_sk_item(sk, pair, item, wi); ++item) {
       const int buf = item & 1;
       int b, h0, w0, n0;
-      tile_coords(pt, b, h0, w0, n0);
+      tile_coords(wi.tile, b, h0, w0, n0);
       const int h = h0 + (row >> tw_log2), w = w0 + (row & (TW - 1));
-      const bool valid = (h < H) && (w < W) && b * tiles_h * tiles_w + (h0 / TH) * tiles_w + (w0 / TW) < 2 * (sk.n_ptiles / sk.n_ntiles);
+      const bool valid = (h < H) && (w < W);
       const size_t pix = ((size_t)b * H + h) * W + w;
-      const bool tail_part = k0 > 0;                      // this pair's FIRST item: the rest of a tile another pair heads
-      const bool head_part = k0 == 0 && k1 < sk.kiters;   // this pair's LAST item: the next pair holds the tail
       tc::mbar_wait(&tmem_full_bar[buf], (item >> 1) & 1);
       tc::tc_fence_after();
-      float* part = sk.ws + (((size_t)(tail_part ? pair : pair + 1) * 2 + crank) * kBM + row) * BN;
-      if (head_part) {                                    // the neighbour finished its tail long ago; acquire its data
-        const int* f = sk.flags + (pair + 1) * 2 + crank;
-        while (*reinterpret_cast<const volatile int*>(f) == 0) __nanosleep(64);
-        __threadfence();
+      if (wi.left_idx < 0) {
+        // ---- whole tile: fused epilogue straight from TMEM
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + c * 32, v);
+          tc::tmem_ld_wait();
+          const int co = n0 + c * 32;
+          if (!valid || co >= Cout) continue;
+          float4* dst = reinterpret_cast<float4*>(y + pix * Cout + co);
+          const float4* msk = reinterpret_cast<const float4*>(mask_src + pix * Cout + co);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            if (bias != nullptr) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + co) + j);
+              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            }
+            if (flags & kAccum) {
+              const float4 p = dst[j];
+              o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+            }
+            if (flags & kRelu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            if (flags & kMask) {
+              const float4 mm = __ldg(msk + j);
+              o.x = mm.x > 0.f ? o.x : 0.f; o.y = mm.y > 0.f ? o.y : 0.f; o.z = mm.z > 0.f ? o.z : 0.f; o.w = mm.w > 0.f ? o.w : 0.f;
+            }
+            if (flags & kRound) { o.x = rna_tf32(o.x); o.y = rna_tf32(o.y); o.z = rna_tf32(o.z); o.w = rna_tf32(o.w); }
+            dst[j] = o;
+          }
+        }
+        tc::tc_fence_before();
+        tc::mbar_arrive_leader(&tmem_empty_bar[buf]);
+        continue;
       }
+      // ---- K slice of a leftover tile: publish the partial, wait for the other slices, reduce my column chunks
+      float* part = sk.ws + ((((size_t)wi.left_idx * sk.slices + wi.slice) * 2 + crank) * kBM + row) * BN;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + c * 32, v);
         tc::tmem_ld_wait();
-        if (tail_part) {
-          float4* dstp = reinterpret_cast<float4*>(part + c * 32);
+        float4* dstp = reinterpret_cast<float4*>(part + c * 32);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) dstp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          continue;
+        for (int j = 0; j < 8; ++j) dstp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+      tc::tc_fence_before();
+      tc::mbar_arrive_leader(&tmem_empty_bar[buf]);
+      int* counter = sk.flags + wi.left_idx * 2 + crank;
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64) atomicAdd(counter, 1);
+      while (*reinterpret_cast<const volatile int*>(counter) < sk.slices) __nanosleep(64);
+      __threadfence();
+      // 16 chunks of 16 columns; slice s reduces chunks s, s + slices, ...  (fixed summation order: slice 0, 1, ...)
+      for (int ch = wi.slice; ch < BN / 16; ch += sk.slices) {
+        float acc16[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) acc16[e] = 0.f;
+        for (int sl = 0; sl < sk.slices; ++sl) {
+          const float4* src = reinterpret_cast<const float4*>(
+              sk.ws + ((((size_t)wi.left_idx * sk.slices + sl) * 2 + crank) * kBM + row) * BN + ch * 16);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 pp = __ldcg(src + j);
+            acc16[4 * j] += pp.x; acc16[4 * j + 1] += pp.y; acc16[4 * j + 2] += pp.z; acc16[4 * j + 3] += pp.w;
+          }
         }
-        const int co = n0 + c * 32;
+        const int co = n0 + ch * 16;
         if (!valid || co >= Cout) continue;
         float4* dst = reinterpret_cast<float4*>(y + pix * Cout + co);
         const float4* msk = reinterpret_cast<const float4*>(mask_src + pix * Cout + co);
-        const float4* prt = reinterpret_cast<const float4*>(part + c * 32);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          if (head_part) {
-            const float4 pp = __ldcg(prt + j);
-            o.x += pp.x; o.y += pp.y; o.z += pp.z; o.w += pp.w;
-          }
+        for (int j = 0; j < 4; ++j) {
+          float4 o = make_float4(acc16[4 * j], acc16[4 * j + 1], acc16[4 * j + 2], acc16[4 * j + 3]);
           if (bias != nullptr) {
             const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + co) + j);
             o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
@@ -494,16 +545,6 @@ conv3x3_tf32_2cta_sk_kernel(const __grid_constant__ CUtensorMap map_x, const __g
           dst[j] = o;
         }
       }
-      tc::tc_fence_before();
-      tc::mbar_arrive_leader(&tmem_empty_bar[buf]);       // 128 threads x 2 CTAs -> the leader may reuse this accumulator
-      if (tail_part) {                                    // publish the partial: all 128 rows written, then the flag
-        __threadfence();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (threadIdx.x == 64) {
-          __threadfence();
-          atomicExch(sk.flags + pair * 2 + crank, 1);
-        }
-      }
     }
   }
   tc::tc_fence_before();
@@ -512,7 +553,7 @@ conv3x3_tf32_2cta_sk_kernel(const __grid_constant__ CUtensorMap map_x, const __g
   if (warp == 1) tc::tmem_dealloc_2sm(tmem_base, 2 * BN);
 }
 
-static void* g_sk_ws = nullptr;          // [74][2][128][256] fp32 partials + flags, allocated once per process
+static void* g_sk_ws = nullptr;          // partial accumulators + arrival counters, allocated once per process
 static size_t g_sk_ws_bytes = 0;
 
 template <int STAGES>
@@ -523,7 +564,6 @@ static int launch_conv_2cta_sk(const CUtensorMap& mx, const CUtensorMap& mw, con
   const int smem = STAGES * (kBM + 128) * tc::kTileKBytes + 1024;
   auto kern = conv3x3_tf32_2cta_sk_kernel<STAGES>;
   ODW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  ODW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 0));
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(192);
   cfg.dynamicSmemBytes = smem;
@@ -535,7 +575,7 @@ static int launch_conv_2cta_sk(const CUtensorMap& mx, const CUtensorMap& mw, con
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  static int max_pairs = -1;             // pairs that are guaranteed co-resident (the schedule spins on a neighbour)
+  static int max_pairs = -1;             // pairs that are guaranteed co-resident (leftover slices wait for each other)
   if (max_pairs < 0) {
     cfg.gridDim = dim3(2 * (ODW_NUM_SMS / 2));
     int n = 0;
@@ -546,21 +586,22 @@ static int launch_conv_2cta_sk(const CUtensorMap& mx, const CUtensorMap& mw, con
   sk.n_ntiles = Cout / 256;
   sk.n_ptiles = (total_tiles / 2) * sk.n_ntiles;
   sk.kiters = 9 * (Cin / tc::kTileK);
-  const int np = min(max_pairs, min(ODW_NUM_SMS / 2, sk.n_ptiles));
-  if (np < 8) return 0;                  // not enough resident pairs: caller uses the one-tile-per-pair kernel
-  const long long total = (long long)sk.n_ptiles * sk.kiters;
-  sk.per_pair = (int)((total + np - 1) / np);
-  if (sk.per_pair < sk.kiters) return 0; // a tile would span three pairs: not handled
-  const size_t need = (size_t)(np + 1) * 2 * kBM * 256 * sizeof(float) + (size_t)(np + 2) * 2 * sizeof(int);
+  sk.np = min(max_pairs, min(ODW_NUM_SMS / 2, sk.n_ptiles));
+  if (sk.np < 8) return 0;               // not enough resident pairs: caller uses the one-tile-per-pair kernel
+  sk.rounds = sk.n_ptiles / sk.np;
+  sk.left = sk.n_ptiles - sk.rounds * sk.np;
+  sk.slices = sk.left > 0 ? min(sk.np / sk.left, min(16, sk.kiters)) : 0;
+  const size_t ws_floats = (size_t)max(sk.left * sk.slices, 1) * 2 * kBM * 256;
+  const size_t need = ws_floats * sizeof(float) + (size_t)(sk.left + 1) * 2 * sizeof(int);
   if (g_sk_ws_bytes < need) {
     if (g_sk_ws) cudaFree(g_sk_ws);
     ODW_CUDA(cudaMalloc(&g_sk_ws, need));
     g_sk_ws_bytes = need;
   }
   sk.ws = reinterpret_cast<float*>(g_sk_ws);
-  sk.flags = reinterpret_cast<int*>(reinterpret_cast<char*>(g_sk_ws) + (size_t)(np + 1) * 2 * kBM * 256 * sizeof(float));
-  ODW_CUDA(cudaMemsetAsync(sk.flags, 0, (size_t)(np + 2) * 2 * sizeof(int), st));
-  cfg.gridDim = dim3(2 * np);
+  sk.flags = reinterpret_cast<int*>(reinterpret_cast<char*>(g_sk_ws) + ws_floats * sizeof(float));
+  if (sk.left > 0) ODW_CUDA(cudaMemsetAsync(sk.flags, 0, (size_t)(sk.left + 1) * 2 * sizeof(int), st));
+  cfg.gridDim = dim3(2 * sk.np);
   ODW_CUDA(cudaLaunchKernelEx(&cfg, kern, mx, mw, bias, msk, y, H, W, Cin, Cout, best_log2, tiles_w, tiles_h, dil, flags, sk));
   *used = true;
   return 0;
