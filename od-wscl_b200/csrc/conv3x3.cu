@@ -354,14 +354,23 @@ __device__ __forceinline__ bool conv_sk_item(const ConvSkParams& sk, int pair, i
   return false;
 }
 
-template <int STAGES>
+// HALO: a k-iteration is (tap ROW r, 32-channel slab) and stages ONE halo row of 128 + 2*dil pixels plus the three weight
+// tiles of the row's taps; the three column taps read the row through descriptors shifted by q*dil rows of 128 bytes
+// (the UMMA swizzle is a function of the absolute shared-memory address, so a window sliding by whole rows over the
+// TMA-written image needs no base-offset field -- verified exact).  The A operand is then staged once per 3 taps:
+// operand bytes per SM drop from 32 KB to 21.6 KB per tap.  Needs 128 x 1 pixel tiles (tw_log2 == 7).  Measured neutral
+// (752 vs 752 TF/s on an evenly dividing shape, 659 vs 679 at 76 rows): operand staging is no longer the limiter of the
+// pair kernel, so it stays off unless ODWSCL_CONV_HALO=1.
+template <int STAGES, bool HALO>
 __global__ void __launch_bounds__(192, 1)
 conv3x3_tf32_2cta_sk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                             const float* __restrict__ bias, const float* __restrict__ mask_src, float* __restrict__ y,
                             int H, int W, int Cin, int Cout, int tw_log2, int tiles_w, int tiles_h, int dil, int flags,
                             const ConvSkParams sk) {
-  constexpr int BN = 256, A_BYTES = kBM * tc::kTileKBytes, B_BYTES = (BN / 2) * tc::kTileKBytes;
+  constexpr int BN = 256, B_TILE = (BN / 2) * tc::kTileKBytes;
+  constexpr int A_BYTES = HALO ? 17 * 1024 : kBM * tc::kTileKBytes, B_BYTES = (HALO ? 3 : 1) * B_TILE;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  const uint32_t stage_tx = HALO ? (uint32_t)(128 + 2 * dil) * 128u + B_BYTES : (uint32_t)STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2];
@@ -404,15 +413,23 @@ conv3x3_tf32_2cta_sk_kernel(const __grid_constant__ CUtensorMap map_x, const __g
       for (int item = 0; conv_sk_item(sk, pair, item, wi); ++item) {
         int b, h0, w0, n0;
         tile_coords(wi.tile, b, h0, w0, n0);
-        int tap = wi.k0 / cchunks, cc = wi.k0 - tap * cchunks;
+        int tap = wi.k0 / cchunks, cc = wi.k0 - tap * cchunks;      // HALO: `tap` counts tap ROWS
         for (int kk = wi.k0; kk < wi.k1; ++kk, ++it) {
           const int s = it % STAGES;
           tc::mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
-          if (crank == 0) tc::mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
+          if (crank == 0) tc::mbar_arrive_expect_tx(&full_bar[s], 2 * stage_tx);
           uint8_t* a = tiles + (size_t)s * STAGE_BYTES;
-          const int r = tap / 3, q = tap - 3 * r;
-          tc::tma_load_4d_2sm(a, &map_x, &full_bar[s], cc * tc::kTileK, w0 + (q - 1) * dil, h0 + (r - 1) * dil, b);
-          tc::tma_load_2d_2sm(a + A_BYTES, &map_w, &full_bar[s], tap * Cin + cc * tc::kTileK, n0 + (int)crank * (BN / 2));
+          if (HALO) {
+            tc::tma_load_4d_2sm(a, &map_x, &full_bar[s], cc * tc::kTileK, w0 - dil, h0 + (tap - 1) * dil, b);
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+              tc::tma_load_2d_2sm(a + A_BYTES + q * B_TILE, &map_w, &full_bar[s], (tap * 3 + q) * Cin + cc * tc::kTileK,
+                                  n0 + (int)crank * (BN / 2));
+          } else {
+            const int r = tap / 3, q = tap - 3 * r;
+            tc::tma_load_4d_2sm(a, &map_x, &full_bar[s], cc * tc::kTileK, w0 + (q - 1) * dil, h0 + (r - 1) * dil, b);
+            tc::tma_load_2d_2sm(a + A_BYTES, &map_w, &full_bar[s], tap * Cin + cc * tc::kTileK, n0 + (int)crank * (BN / 2));
+          }
           if (++cc == cchunks) { cc = 0; ++tap; }
         }
       }
@@ -432,10 +449,21 @@ conv3x3_tf32_2cta_sk_kernel(const __grid_constant__ CUtensorMap map_x, const __g
           tc::mbar_wait(&full_bar[s], (it / STAGES) & 1);
           tc::tc_fence_after();
           const uint32_t a = tc::smem_u32(tiles + (size_t)s * STAGE_BYTES);
-          const uint64_t ad = tc::umma_desc_sw128(a), bd = tc::umma_desc_sw128(a + A_BYTES);
+          if (HALO) {
 #pragma unroll
-          for (int k = 0; k < tc::kTileK / tc::kUmmaK; ++k)
-            tc::umma_tf32_2sm(acc, ad + 2 * k, bd + 2 * k, idesc, (kk != wi.k0) || (k != 0));
+            for (int q = 0; q < 3; ++q) {
+              const uint64_t ad = tc::umma_desc_sw128(a + (uint32_t)(q * dil) * 128u);
+              const uint64_t bd = tc::umma_desc_sw128(a + A_BYTES + q * B_TILE);
+#pragma unroll
+              for (int k = 0; k < tc::kTileK / tc::kUmmaK; ++k)
+                tc::umma_tf32_2sm(acc, ad + 2 * k, bd + 2 * k, idesc, (kk != wi.k0) || (q | k) != 0);
+            }
+          } else {
+            const uint64_t ad = tc::umma_desc_sw128(a), bd = tc::umma_desc_sw128(a + A_BYTES);
+#pragma unroll
+            for (int k = 0; k < tc::kTileK / tc::kUmmaK; ++k)
+              tc::umma_tf32_2sm(acc, ad + 2 * k, bd + 2 * k, idesc, (kk != wi.k0) || (k != 0));
+          }
           tc::umma_commit_2sm_mc(&empty_bar[s], 3);
         }
         tc::umma_commit_2sm_mc(&tmem_full_bar[buf], 3);
@@ -556,13 +584,13 @@ conv3x3_tf32_2cta_sk_kernel(const __grid_constant__ CUtensorMap map_x, const __g
 static void* g_sk_ws = nullptr;          // partial accumulators + arrival counters, allocated once per process
 static size_t g_sk_ws_bytes = 0;
 
-template <int STAGES>
+template <int STAGES, bool HALO>
 static int launch_conv_2cta_sk(const CUtensorMap& mx, const CUtensorMap& mw, const float* bias, const float* msk, float* y,
                                int H, int W, int Cin, int Cout, int best_log2, int tiles_w, int tiles_h, int total_tiles,
                                int dil, int flags, cudaStream_t st, bool* used) {
   *used = false;
-  const int smem = STAGES * (kBM + 128) * tc::kTileKBytes + 1024;
-  auto kern = conv3x3_tf32_2cta_sk_kernel<STAGES>;
+  const int smem = STAGES * (HALO ? 17 * 1024 + 3 * 128 * tc::kTileKBytes : (kBM + 128) * tc::kTileKBytes) + 1024;
+  auto kern = conv3x3_tf32_2cta_sk_kernel<STAGES, HALO>;
   ODW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(192);
@@ -585,7 +613,7 @@ static int launch_conv_2cta_sk(const CUtensorMap& mx, const CUtensorMap& mw, con
   ConvSkParams sk;
   sk.n_ntiles = Cout / 256;
   sk.n_ptiles = (total_tiles / 2) * sk.n_ntiles;
-  sk.kiters = 9 * (Cin / tc::kTileK);
+  sk.kiters = (HALO ? 3 : 9) * (Cin / tc::kTileK);
   sk.np = min(max_pairs, min(ODW_NUM_SMS / 2, sk.n_ptiles));
   if (sk.np < 8) return 0;               // not enough resident pairs: caller uses the one-tile-per-pair kernel
   sk.rounds = sk.n_ptiles / sk.np;
@@ -674,8 +702,18 @@ int launch_conv(const float* x, int B, int H, int W, int Cin, const float* wk, c
     if (pair) {
       if (conv_env("ODWSCL_CONV_PERSIST", 1) != 0) {
         bool used = false;
-        rc = launch_conv_2cta_sk<6>(mx, mw, bias, msk, y, H, W, Cin, Cout, best_log2, tiles_w, tiles_h, total_tiles, dil,
-                                    flags, st, &used);
+        if (best_log2 == 7 && dil <= 4 && conv_env("ODWSCL_CONV_HALO", 0) != 0) {
+          // 128 x 1 tiles: one halo row per (tap row, slab), the three column taps slide over it
+          CUtensorMap mxh;
+          const uint32_t bxh[4] = {32, (uint32_t)(128 + 2 * dil), 1, 1};
+          rc = tc::make_tmap_f32(&mxh, x, 4, dx, sx, bxh);
+          if (rc) return rc;
+          rc = launch_conv_2cta_sk<3, true>(mxh, mw, bias, msk, y, H, W, Cin, Cout, best_log2, tiles_w, tiles_h,
+                                            total_tiles, dil, flags, st, &used);
+        } else {
+          rc = launch_conv_2cta_sk<6, false>(mx, mw, bias, msk, y, H, W, Cin, Cout, best_log2, tiles_w, tiles_h,
+                                             total_tiles, dil, flags, st, &used);
+        }
         if (rc != 0 || used) return rc;
       }
       return launch_conv_2cta<6>(mx, mw, bias, msk, y, H, W, Cin, Cout, best_log2, tiles_w, tiles_h, total_tiles, dil,

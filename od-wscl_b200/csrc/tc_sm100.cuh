@@ -134,6 +134,12 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// Same, for a tile whose first row is NOT at the start of a 1024-byte swizzle atom (a window sliding by whole 128-byte
+// rows over a larger swizzled image, e.g. the tap-shifted views of one convolution halo row): bits [49,52) carry the
+// row phase (start >> 7) & 7 ("matrix base offset").
+__device__ __forceinline__ uint64_t umma_desc_sw128_rowshift(uint32_t saddr, uint32_t base_offset) {
+  return umma_desc_sw128(saddr) | ((uint64_t)(base_offset & 7u) << 49);
+}
 // MN-major operand (the contraction index is the OUTER, strided one -- e.g. pixels of an NHWC tensor when the
 // GEMM contracts over pixels).  For 32-bit (tf32) data the only MN-major layout the tensor core accepts is
 // SWIZZLE_128B_BASE32B (layout type 1; "for mn-major tf32 operands, SW128_32B is the only available smem

@@ -171,3 +171,20 @@ def test_conv3x3_wgrad(capi, B, H, W, Cin, Cout, dil):
     tol = 3e-5 * (B * H * W) ** 0.5
     torch.testing.assert_close(dw.permute(0, 3, 1, 2), gw.float(), rtol=1e-5, atol=tol)
     torch.testing.assert_close(db, gb.float(), rtol=1e-5, atol=tol)
+
+
+@pytest.mark.parametrize("env", [{"ODWSCL_CONV_PERSIST": "0"}, {"ODWSCL_CONV_2CTA": "0"}, {"ODWSCL_CONV_HALO": "1"},
+                                 {"ODWSCL_CONV_2CTA": "0", "ODWSCL_CONV_CLUSTER": "2"},
+                                 {"ODWSCL_CONV_2CTA": "0", "ODWSCL_CONV_MT": "2"}])
+def test_conv3x3_kernel_variants_exact(capi, env, monkeypatch):
+    """Every conv kernel variant (one tile per CTA pair, single CTA, halo-row operand, weight multicast, two accumulators)
+    is exact on exactly-representable inputs, including the split-K tail of the persistent schedule."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    for (B, H, W, Cin, Cout, dil) in [(2, 76, 128, 256, 512, 2), (1, 150, 128, 128, 256, 1), (2, 40, 256, 64, 256, 1)]:
+        g = torch.Generator().manual_seed(H + Cin)
+        x = q(torch.randn(B, H, W, Cin, generator=g)).cuda()
+        w = q(torch.randn(Cout, Cin, 3, 3, generator=g) * 0.5, 16).cuda()
+        b = q(torch.randn(Cout, generator=g)).cuda()
+        got = capi.conv3x3_nhwc(x, w.permute(0, 2, 3, 1).contiguous(), b, dilation=dil, flags=capi.CONV_RELU)
+        assert torch.equal(got, ref_conv(x, w, b, dil).clamp_min(0))
