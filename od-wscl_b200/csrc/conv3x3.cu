@@ -342,15 +342,21 @@ struct ConvSkParams {
 
 struct ConvSkItem { int tile, k0, k1, left_idx, slice; };   // left_idx < 0: a whole tile
 
+// Work list of one pair: its K slice of a leftover tile FIRST (the partial is published early and reduced at the very
+// end, when every other slice has long arrived -- nobody waits), then the whole tiles round by round.
 __device__ __forceinline__ bool conv_sk_item(const ConvSkParams& sk, int pair, int idx, ConvSkItem& it) {
-  if (idx < sk.rounds) { it.tile = idx * sk.np + pair; it.k0 = 0; it.k1 = sk.kiters; it.left_idx = -1; it.slice = 0; return true; }
-  if (idx == sk.rounds && sk.left > 0 && pair < sk.left * sk.slices) {
-    it.left_idx = pair / sk.slices; it.slice = pair - it.left_idx * sk.slices;
-    it.tile = sk.rounds * sk.np + it.left_idx;
-    it.k0 = (int)((long long)it.slice * sk.kiters / sk.slices);
-    it.k1 = (int)((long long)(it.slice + 1) * sk.kiters / sk.slices);
-    return true;
+  const bool has_tail = sk.left > 0 && pair < sk.left * sk.slices;
+  if (has_tail) {
+    if (idx == 0) {
+      it.left_idx = pair / sk.slices; it.slice = pair - it.left_idx * sk.slices;
+      it.tile = sk.rounds * sk.np + it.left_idx;
+      it.k0 = (int)((long long)it.slice * sk.kiters / sk.slices);
+      it.k1 = (int)((long long)(it.slice + 1) * sk.kiters / sk.slices);
+      return true;
+    }
+    --idx;
   }
+  if (idx < sk.rounds) { it.tile = idx * sk.np + pair; it.k0 = 0; it.k1 = sk.kiters; it.left_idx = -1; it.slice = 0; return true; }
   return false;
 }
 
@@ -517,7 +523,7 @@ conv3x3_tf32_2cta_sk_kernel(const __grid_constant__ CUtensorMap map_x, const __g
         tc::mbar_arrive_leader(&tmem_empty_bar[buf]);
         continue;
       }
-      // ---- K slice of a leftover tile: publish the partial, wait for the other slices, reduce my column chunks
+      // ---- K slice of a leftover tile: publish the partial now, reduce after the whole tiles
       float* part = sk.ws + ((((size_t)wi.left_idx * sk.slices + wi.slice) * 2 + crank) * kBM + row) * BN;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
@@ -529,33 +535,37 @@ conv3x3_tf32_2cta_sk_kernel(const __grid_constant__ CUtensorMap map_x, const __g
       }
       tc::tc_fence_before();
       tc::mbar_arrive_leader(&tmem_empty_bar[buf]);
-      int* counter = sk.flags + wi.left_idx * 2 + crank;
       __threadfence();
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (threadIdx.x == 64) atomicAdd(counter, 1);
+      if (threadIdx.x == 64) atomicAdd(sk.flags + wi.left_idx * 2 + crank, 1);
+    }
+    // ---- reduction of the leftover tile this pair holds a slice of: 32 chunks of 8 columns, slice s takes chunks
+    // s, s + slices, ...; fixed summation order (slice 0, 1, ...), then the fused epilogue
+    if (conv_sk_item(sk, pair, 0, wi) && wi.left_idx >= 0) {
+      int b, h0, w0, n0;
+      tile_coords(wi.tile, b, h0, w0, n0);
+      const int h = h0 + (row >> tw_log2), w = w0 + (row & (TW - 1));
+      const bool valid = (h < H) && (w < W);
+      const size_t pix = ((size_t)b * H + h) * W + w;
+      const int* counter = sk.flags + wi.left_idx * 2 + crank;
       while (*reinterpret_cast<const volatile int*>(counter) < sk.slices) __nanosleep(64);
       __threadfence();
-      // 16 chunks of 16 columns; slice s reduces chunks s, s + slices, ...  (fixed summation order: slice 0, 1, ...)
-      for (int ch = wi.slice; ch < BN / 16; ch += sk.slices) {
-        float acc16[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) acc16[e] = 0.f;
+      for (int ch = wi.slice; ch < BN / 8; ch += sk.slices) {
+        float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
         for (int sl = 0; sl < sk.slices; ++sl) {
           const float4* src = reinterpret_cast<const float4*>(
-              sk.ws + ((((size_t)wi.left_idx * sk.slices + sl) * 2 + crank) * kBM + row) * BN + ch * 16);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 pp = __ldcg(src + j);
-            acc16[4 * j] += pp.x; acc16[4 * j + 1] += pp.y; acc16[4 * j + 2] += pp.z; acc16[4 * j + 3] += pp.w;
-          }
+              sk.ws + ((((size_t)wi.left_idx * sk.slices + sl) * 2 + crank) * kBM + row) * BN + ch * 8);
+          const float4 p0 = __ldcg(src), p1 = __ldcg(src + 1);
+          s0.x += p0.x; s0.y += p0.y; s0.z += p0.z; s0.w += p0.w;
+          s1.x += p1.x; s1.y += p1.y; s1.z += p1.z; s1.w += p1.w;
         }
-        const int co = n0 + ch * 16;
+        const int co = n0 + ch * 8;
         if (!valid || co >= Cout) continue;
         float4* dst = reinterpret_cast<float4*>(y + pix * Cout + co);
         const float4* msk = reinterpret_cast<const float4*>(mask_src + pix * Cout + co);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float4 o = make_float4(acc16[4 * j], acc16[4 * j + 1], acc16[4 * j + 2], acc16[4 * j + 3]);
+        for (int j = 0; j < 2; ++j) {
+          float4 o = j ? s1 : s0;
           if (bias != nullptr) {
             const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + co) + j);
             o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
@@ -618,7 +628,7 @@ static int launch_conv_2cta_sk(const CUtensorMap& mx, const CUtensorMap& mw, con
   if (sk.np < 8) return 0;               // not enough resident pairs: caller uses the one-tile-per-pair kernel
   sk.rounds = sk.n_ptiles / sk.np;
   sk.left = sk.n_ptiles - sk.rounds * sk.np;
-  sk.slices = sk.left > 0 ? min(sk.np / sk.left, min(16, sk.kiters)) : 0;
+  sk.slices = sk.left > 0 ? min(sk.np / sk.left, min(32, sk.kiters)) : 0;
   const size_t ws_floats = (size_t)max(sk.left * sk.slices, 1) * 2 * kBM * 256;
   const size_t need = ws_floats * sizeof(float) + (size_t)(sk.left + 1) * 2 * sizeof(int);
   if (g_sk_ws_bytes < need) {
