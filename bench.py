@@ -27,6 +27,8 @@ sys.path.insert(0, ROOT)
 
 IMG_W, IMG_H, N_PROP, B_PER_GPU, NUM_CLASSES = 1000, 600, 2000, 2, 21
 METRIC = "proposals/sec (2000 ROIs/img, 1000x600)"
+WORKLOAD = ("BASELINE configs[1]: bs=2/GPU, 2000 MCG-style proposals/img, 1000x600 (pad 608x1024), VGG16-OICR, 21 classes, "
+            "fwd+bwd+SGD")
 
 
 def parse():
@@ -123,7 +125,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "proposals/s", "n_gpus": args.gpus,
             "steps": max(1, min(args.steps, 3)), "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": "configs[1] shape, bounded CPU sample: " + sample},
+            "config": {"workload": WORKLOAD, "images_per_gpu": B_PER_GPU, "proposals_per_image": N_PROP,
+                       "sample": "bounded CPU sample per step: " + sample},
             "cpu_baseline": {"value": rate, "unit": "proposals/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": "proposals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -390,7 +393,7 @@ def run_ours(args):
             "warmup": n_warm, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "fp32" if args.strict_fp32 else "fp32 storage, tf32 tensor-core conv/GEMM (the reference's torch-1.7.1 default); hand-written kernels fp32",
             "data": "synthetic",
-            "config": {"workload": "BASELINE configs[1]: bs=2/GPU, 2000 MCG-style proposals/img, 1000x600 (pad 608x1024), VGG16-OICR, 21 classes, fwd+bwd+SGD",
+            "config": {"workload": WORKLOAD,
                        "images_per_gpu": B_PER_GPU, "proposals_per_image": N_PROP, "parallelism": "dp%d" % world,
                        "host_syncs_per_step": 1 if args.sync_k else 0, "skipped_updates": [skipped, skipped_e2e],
                        "l2": "per-step working set (>=1.6 GB of activations) exceeds the 126 MB L2; kernel-alone timings flush L2 with a 256 MB write"},
