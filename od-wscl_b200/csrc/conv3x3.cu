@@ -367,13 +367,14 @@ __device__ __forceinline__ bool conv_sk_item(const ConvSkParams& sk, int pair, i
 // operand bytes per SM drop from 32 KB to 21.6 KB per tap.  Needs 128 x 1 pixel tiles (tw_log2 == 7).  Measured neutral
 // (752 vs 752 TF/s on an evenly dividing shape, 659 vs 679 at 76 rows): operand staging is no longer the limiter of the
 // pair kernel, so it stays off unless ODWSCL_CONV_HALO=1.
-template <int STAGES, bool HALO>
+template <int STAGES, bool HALO, int BN>
 __global__ void __launch_bounds__(192, 1)
 conv3x3_tf32_2cta_sk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                             const float* __restrict__ bias, const float* __restrict__ mask_src, float* __restrict__ y,
                             int H, int W, int Cin, int Cout, int tw_log2, int tiles_w, int tiles_h, int dil, int flags,
                             const ConvSkParams sk) {
-  constexpr int BN = 256, B_TILE = (BN / 2) * tc::kTileKBytes;
+  constexpr int B_TILE = (BN / 2) * tc::kTileKBytes;
+  constexpr int TM_COLS = BN < 32 ? 32 : BN;                  // TMEM columns per accumulator buffer (allocation granule)
   constexpr int A_BYTES = HALO ? 17 * 1024 : kBM * tc::kTileKBytes, B_BYTES = (HALO ? 3 : 1) * B_TILE;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   const uint32_t stage_tx = HALO ? (uint32_t)(128 + 2 * dil) * 128u + B_BYTES : (uint32_t)STAGE_BYTES;
@@ -395,7 +396,7 @@ conv3x3_tf32_2cta_sk_kernel(const __grid_constant__ CUtensorMap map_x, const __g
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&tmem_full_bar[i], 1); tc::mbar_init(&tmem_empty_bar[i], 256); }
     tc::fence_barrier_init();
   }
-  if (warp == 1) tc::tmem_alloc_2sm(&tmem_base_s, 2 * BN);
+  if (warp == 1) tc::tmem_alloc_2sm(&tmem_base_s, 2 * TM_COLS);
   tc::tc_fence_before();
   __syncthreads();
   tc::cluster_sync_all();
@@ -449,7 +450,7 @@ conv3x3_tf32_2cta_sk_kernel(const __grid_constant__ CUtensorMap map_x, const __g
         const int buf = item & 1;
         tc::mbar_wait(&tmem_empty_bar[buf], ((item >> 1) & 1) ^ 1);     // both CTAs drained this accumulator
         tc::tc_fence_after();
-        const uint32_t acc = tmem_base + buf * BN;
+        const uint32_t acc = tmem_base + buf * TM_COLS;
         for (int kk = wi.k0; kk < wi.k1; ++kk, ++it) {
           const int s = it % STAGES;
           tc::mbar_wait(&full_bar[s], (it / STAGES) & 1);
@@ -493,7 +494,7 @@ conv3x3_tf32_2cta_sk_kernel(const __grid_constant__ CUtensorMap map_x, const __g
         // ---- whole tile: fused epilogue straight from TMEM
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
-          tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + c * 32, v);
+          tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * TM_COLS + c * 32, v);
           tc::tmem_ld_wait();
           const int co = n0 + c * 32;
           if (!valid || co >= Cout) continue;
@@ -527,7 +528,7 @@ conv3x3_tf32_2cta_sk_kernel(const __grid_constant__ CUtensorMap map_x, const __g
       float* part = sk.ws + ((((size_t)wi.left_idx * sk.slices + wi.slice) * 2 + crank) * kBM + row) * BN;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
-        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + c * 32, v);
+        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * TM_COLS + c * 32, v);
         tc::tmem_ld_wait();
         float4* dstp = reinterpret_cast<float4*>(part + c * 32);
 #pragma unroll
@@ -588,19 +589,19 @@ conv3x3_tf32_2cta_sk_kernel(const __grid_constant__ CUtensorMap map_x, const __g
   tc::tc_fence_before();
   __syncthreads();
   tc::cluster_sync_all();
-  if (warp == 1) tc::tmem_dealloc_2sm(tmem_base, 2 * BN);
+  if (warp == 1) tc::tmem_dealloc_2sm(tmem_base, 2 * TM_COLS);
 }
 
 static void* g_sk_ws = nullptr;          // partial accumulators + arrival counters, allocated once per process
 static size_t g_sk_ws_bytes = 0;
 
-template <int STAGES, bool HALO>
+template <int STAGES, bool HALO, int BN>
 static int launch_conv_2cta_sk(const CUtensorMap& mx, const CUtensorMap& mw, const float* bias, const float* msk, float* y,
                                int H, int W, int Cin, int Cout, int best_log2, int tiles_w, int tiles_h, int total_tiles,
                                int dil, int flags, cudaStream_t st, bool* used) {
   *used = false;
-  const int smem = STAGES * (HALO ? 17 * 1024 + 3 * 128 * tc::kTileKBytes : (kBM + 128) * tc::kTileKBytes) + 1024;
-  auto kern = conv3x3_tf32_2cta_sk_kernel<STAGES, HALO>;
+  const int smem = STAGES * (HALO ? 17 * 1024 + 3 * (BN / 2) * tc::kTileKBytes : (kBM + BN / 2) * tc::kTileKBytes) + 1024;
+  auto kern = conv3x3_tf32_2cta_sk_kernel<STAGES, HALO, BN>;
   ODW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(192);
@@ -621,7 +622,7 @@ static int launch_conv_2cta_sk(const CUtensorMap& mx, const CUtensorMap& mw, con
     max_pairs = n;
   }
   ConvSkParams sk;
-  sk.n_ntiles = Cout / 256;
+  sk.n_ntiles = Cout / BN;
   sk.n_ptiles = (total_tiles / 2) * sk.n_ntiles;
   sk.kiters = (HALO ? 3 : 9) * (Cin / tc::kTileK);
   sk.np = min(max_pairs, min(ODW_NUM_SMS / 2, sk.n_ptiles));
@@ -629,7 +630,7 @@ static int launch_conv_2cta_sk(const CUtensorMap& mx, const CUtensorMap& mw, con
   sk.rounds = sk.n_ptiles / sk.np;
   sk.left = sk.n_ptiles - sk.rounds * sk.np;
   sk.slices = sk.left > 0 ? min(sk.np / sk.left, min(32, sk.kiters)) : 0;
-  const size_t ws_floats = (size_t)max(sk.left * sk.slices, 1) * 2 * kBM * 256;
+  const size_t ws_floats = (size_t)max(sk.left * sk.slices, 1) * 2 * kBM * BN;
   const size_t need = ws_floats * sizeof(float) + (size_t)(sk.left + 1) * 2 * sizeof(int);
   if (g_sk_ws_bytes < need) {
     if (g_sk_ws) cudaFree(g_sk_ws);
@@ -692,7 +693,8 @@ int launch_conv(const float* x, int B, int H, int W, int Cin, const float* wk, c
   const int total_tiles = B * tiles_h * tiles_w;
   const int n_tiles = odw_cdiv(Cout, BN);
   // CTA pairs (cta_group::2) for the 256-channel tiles; ODWSCL_CONV_2CTA=0 falls back to one CTA per tile
-  const bool pair = BN == 256 && Cout % 256 == 0 && total_tiles % 2 == 0 && conv_env("ODWSCL_CONV_2CTA", 1) != 0;
+  const bool pair = BN >= 64 && Cout % BN == 0 && total_tiles % 2 == 0 && conv_env("ODWSCL_CONV_2CTA", 1) != 0 &&
+                    (BN == 256 || conv_env("ODWSCL_CONV_PERSIST", 1) != 0);
   // two accumulators per CTA (ODWSCL_CONV_MT=2; measured slower at the bench shapes, off by default)
   const bool mt2 = !pair && BN == 256 && conv_env("ODWSCL_CONV_MT", 1) >= 2 && odw_cdiv(total_tiles, 2) * n_tiles >= ODW_NUM_SMS;
   const int cl = (pair || (!mt2 && conv_env("ODWSCL_CONV_CLUSTER", 1) >= 2 && total_tiles % 2 == 0)) ? 2 : 1;
@@ -708,7 +710,7 @@ int launch_conv(const float* x, int B, int H, int W, int Cin, const float* wk, c
   rc = tc::make_tmap_f32(&mw, wk, 2, dw, sw, bw);
   if (rc) return rc;
   const float* msk = mask_src ? mask_src : y;
-  if constexpr (BN == 256) {
+  if constexpr (BN >= 64) {
     if (pair) {
       if (conv_env("ODWSCL_CONV_PERSIST", 1) != 0) {
         bool used = false;
@@ -718,16 +720,17 @@ int launch_conv(const float* x, int B, int H, int W, int Cin, const float* wk, c
           const uint32_t bxh[4] = {32, (uint32_t)(128 + 2 * dil), 1, 1};
           rc = tc::make_tmap_f32(&mxh, x, 4, dx, sx, bxh);
           if (rc) return rc;
-          rc = launch_conv_2cta_sk<3, true>(mxh, mw, bias, msk, y, H, W, Cin, Cout, best_log2, tiles_w, tiles_h,
-                                            total_tiles, dil, flags, st, &used);
+          rc = launch_conv_2cta_sk<3, true, BN>(mxh, mw, bias, msk, y, H, W, Cin, Cout, best_log2, tiles_w, tiles_h,
+                                                total_tiles, dil, flags, st, &used);
         } else {
-          rc = launch_conv_2cta_sk<6, false>(mx, mw, bias, msk, y, H, W, Cin, Cout, best_log2, tiles_w, tiles_h,
-                                             total_tiles, dil, flags, st, &used);
+          rc = launch_conv_2cta_sk<6, false, BN>(mx, mw, bias, msk, y, H, W, Cin, Cout, best_log2, tiles_w, tiles_h,
+                                                 total_tiles, dil, flags, st, &used);
         }
         if (rc != 0 || used) return rc;
       }
-      return launch_conv_2cta<6>(mx, mw, bias, msk, y, H, W, Cin, Cout, best_log2, tiles_w, tiles_h, total_tiles, dil,
-                                 flags, st);
+      if constexpr (BN == 256)
+        return launch_conv_2cta<6>(mx, mw, bias, msk, y, H, W, Cin, Cout, best_log2, tiles_w, tiles_h, total_tiles, dil,
+                                   flags, st);
     }
     if (mt2)
       return launch_conv_inst<BN, 3, 1, 2>(mx, mw, bias, msk, y, H, W, Cin, Cout, best_log2, tiles_w, tiles_h, total_tiles,
