@@ -37,8 +37,8 @@ if [[ $ST == *c* ]]; then
   # full capture of the tcgen05 conv kernel: launches 4.. = timed conv1_2, then skip to conv4_2-shaped ones
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:"conv3x3_tf32_kernel" -s 3 -c 1 \
       -o $OUT/prof_conv_a -f python scripts/bench_conv.py 2 > $OUT/ncu_conv.log 2>&1
-  # conv3_1, conv3_2, conv4_1, conv4_2, conv5_1 run the CTA-pair kernel (13 launches each): 4th timed launch of conv4_2
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"conv3x3_tf32_2cta_sk_kernel" -s 42 -c 1 \
+  # every bench_conv layer runs the persistent CTA-pair kernel (13 launches each): launch 84 = a timed conv4_2
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"conv3x3_tf32_2cta_sk_kernel" -s 84 -c 1 \
       -o $OUT/prof_conv_b -f python scripts/bench_conv.py 2 >> $OUT/ncu_conv.log 2>&1
   echo "ncu conv rc=$?"; ls -la $OUT
 fi
