@@ -31,6 +31,41 @@ class _ReluDropoutFn(torch.autograd.Function):
         return capi.relu_dropout_backward(y, gy.contiguous(), ctx.p), None, None
 
 
+class _Fc6Fn(torch.autograd.Function):
+    """fc6 (classifier.1, [4096,25088] = 411 MB) is applied twice per step: to the [2R,25088] clean+augmented batch and to
+    the few augmented positives of the contrastive branch (weak_head.py:107-112, loss.py:299-310).  Autograd would write
+    the second weight gradient as one more 411 MB tensor and add the two (a 1.2 GB pass).  Here the small call's backward
+    (which runs first: its node is younger) only stashes (grad_out, input); the batch call's backward folds it into its
+    own weight gradient with a beta = 1 GEMM.  If the order is ever the other way round the small call falls back to
+    returning its own gradient, so the result never depends on the assumption."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stash, role):
+        ctx.save_for_backward(x, weight)
+        ctx.stash, ctx.role = stash, role
+        if role == "main":
+            stash["has_main"] = True            # a batch call whose backward will collect the stashed gradients exists
+        return torch.nn.functional.linear(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        g = g.contiguous()
+        gx = g @ weight if ctx.needs_input_grad[0] else None
+        st = ctx.stash
+        if ctx.role == "small" and st.get("has_main", False) and not st.get("main_done", False):
+            st.setdefault("pending", []).append((g, x))
+            return gx, None, None, None, None
+        gw = g.t() @ x
+        gb = g.sum(0)
+        if ctx.role == "main":
+            for gs, xs in st.pop("pending", []):
+                gw.addmm_(gs.t(), xs)
+                gb = gb + gs.sum(0)
+            st["main_done"] = True
+        return gx, gw, gb, None, None
+
+
 class Identity(nn.Module):
     def __init__(self, *args, **kwargs):
         super().__init__()
@@ -110,6 +145,8 @@ class VGG16FC67ROIFeatureExtractor(nn.Module):
         self.sim_drop = DropBlock2D(block_size=1, drop_prob=0.3)
         self.noise_sampler = None      # test hook: callable(shape, device) -> N(0,1) tensor
         self.fuse_relu_dropout = True  # train: ReLU + Dropout of fc6 / fc7 as one in-place kernel
+        self.merge_fc6_wgrad = True    # train: the two fc6 weight gradients of a step leave as one tensor (_Fc6Fn)
+        self._fc6_stash = None
         self.fuse_clean_aug = True     # train: ROIPool + DropBlock into one [2R,...] batch, fc6/fc7 once
         if init_weights:
             for m in self.modules():
@@ -117,14 +154,18 @@ class VGG16FC67ROIFeatureExtractor(nn.Module):
                     nn.init.normal_(m.weight, 0, 0.01)
                     nn.init.constant_(m.bias, 0)
 
-    def run_classifier(self, x):
+    def run_classifier(self, x, role=None):
         """self.classifier(x) (vgg16.py:122-130).  In training on the GPU the two ReLU + Dropout pairs run as one fused
-        in-place kernel each; the Linear layers stay with cuBLAS.  Same parameters, same state-dict keys."""
+        in-place kernel each; the Linear layers stay with cuBLAS.  Same parameters, same state-dict keys.  `role`
+        ("main" / "small") routes fc6 through _Fc6Fn so its two weight gradients of a step are produced as one."""
         c = self.classifier
         if not (self.training and self.fuse_relu_dropout and x.is_cuda and x.dtype == torch.float32):
             return c(x)
         for lin, drop in ((c[1], c[3]), (c[4], c[6])):
-            x = torch.nn.functional.linear(x, lin.weight, lin.bias)
+            if lin is c[1] and role is not None and self._fc6_stash is not None and lin.weight.requires_grad:
+                x = _Fc6Fn.apply(x, lin.weight, lin.bias, self._fc6_stash, role)
+            else:
+                x = torch.nn.functional.linear(x, lin.weight, lin.bias)
             if x.numel() % 4 == 0 and x.numel() > 0:
                 seed = int(torch.randint(0, 2 ** 62, (1,)).item())       # CPU generator: no device sync
                 x = _ReluDropoutFn.apply(x, float(drop.p), seed)
@@ -133,6 +174,7 @@ class VGG16FC67ROIFeatureExtractor(nn.Module):
         return x
 
     def forward(self, x, proposals):                     # vgg16.py:148-153
+        self._fc6_stash = None
         pooled_feat = self.pooler(x, proposals)
         x = self.run_classifier(pooled_feat.view(pooled_feat.shape[0], -1))
         return x, pooled_feat
@@ -159,7 +201,8 @@ class VGG16FC67ROIFeatureExtractor(nn.Module):
             centres = (torch.rand(R, ph, pw, device=rois.device) < gamma).float()
         stash = {}
         buf = pool_and_augment(x[0].float(), rois, (ph, pw), pool.spatial_scale, centres.contiguous(), db.block_size, stash)
-        feats = self.run_classifier(buf.view(2 * R, -1))
+        self._fc6_stash = {} if self.merge_fc6_wgrad else None      # one stash per step: main call here, small calls later
+        feats = self.run_classifier(buf.view(2 * R, -1), role="main" if self._fc6_stash is not None else None)
         clean, aug = split_rows(feats, R)
         pooled = buf.detach()[:R]
         pooled._odw_gather = lambda rows: gather_rows(buf, rows, R, stash)
@@ -169,7 +212,7 @@ class VGG16FC67ROIFeatureExtractor(nn.Module):
         return self.pooler(x, proposals)
 
     def forward_neck(self, x):                           # vgg16.py:159-162
-        return self.run_classifier(x.view(x.shape[0], -1))
+        return self.run_classifier(x.view(x.shape[0], -1), role="small" if self._fc6_stash is not None else None)
 
     def forward_dropblock(self, pooled_feats, proposals):  # vgg16.py:165-167
         return self.dropblock(pooled_feats)
