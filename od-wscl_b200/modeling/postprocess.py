@@ -15,27 +15,24 @@ BBOX_XFORM_CLIP = math.log(1000.0 / 16)
 
 
 def decode_boxes(rel_codes, boxes, weights=(10.0, 10.0, 5.0, 5.0)):
-    """BoxCoder.decode: rel_codes [N, C*4], boxes [N,4] -> [N, C*4] (same operation order as the reference)."""
-    boxes = boxes.to(rel_codes.dtype)
-    widths = boxes[:, 2] - boxes[:, 0] + 1
-    heights = boxes[:, 3] - boxes[:, 1] + 1
-    ctr_x = boxes[:, 0] + 0.5 * widths
-    ctr_y = boxes[:, 1] + 0.5 * heights
-    wx, wy, ww, wh = weights
-    dx = rel_codes[:, 0::4] / wx
-    dy = rel_codes[:, 1::4] / wy
-    dw = torch.clamp(rel_codes[:, 2::4] / ww, max=BBOX_XFORM_CLIP)
-    dh = torch.clamp(rel_codes[:, 3::4] / wh, max=BBOX_XFORM_CLIP)
-    pred_ctr_x = dx * widths[:, None] + ctr_x[:, None]
-    pred_ctr_y = dy * heights[:, None] + ctr_y[:, None]
-    pred_w = torch.exp(dw) * widths[:, None]
-    pred_h = torch.exp(dh) * heights[:, None]
-    out = torch.zeros_like(rel_codes)
-    out[:, 0::4] = pred_ctr_x - 0.5 * pred_w
-    out[:, 1::4] = pred_ctr_y - 0.5 * pred_h
-    out[:, 2::4] = pred_ctr_x + 0.5 * pred_w - 1
-    out[:, 3::4] = pred_ctr_y + 0.5 * pred_h - 1
-    return out
+    """BoxCoder.decode (modeling/box_coder.py:52-95): deltas [N, C*4] applied to reference boxes [N,4] -> [N, C*4].
+    Written over a [N,C,4] view; every element goes through the reference's operations in the reference's order
+    (+1 widths, centre + 0.5 w, delta / weight, clamp of dw / dh at log(1000/16), exp, the "- 1" on x2 / y2)."""
+    ref = boxes.to(rel_codes.dtype)
+    n = rel_codes.shape[0]
+    d = rel_codes.view(n, -1, 4)
+    size = ref[:, 2:4] - ref[:, 0:2] + 1                        # [N,2] (w, h)
+    centre = ref[:, 0:2] + 0.5 * size                           # [N,2]
+    w_xy = torch.as_tensor(weights[0:2], dtype=d.dtype, device=d.device)
+    w_wh = torch.as_tensor(weights[2:4], dtype=d.dtype, device=d.device)
+    shift = d[:, :, 0:2] / w_xy                                 # dx, dy
+    grow = torch.clamp(d[:, :, 2:4] / w_wh, max=BBOX_XFORM_CLIP)  # dw, dh
+    new_centre = shift * size[:, None, :] + centre[:, None, :]
+    new_size = torch.exp(grow) * size[:, None, :]
+    out = torch.empty_like(d)
+    out[:, :, 0:2] = new_centre - 0.5 * new_size
+    out[:, :, 2:4] = new_centre + 0.5 * new_size - 1
+    return out.view(n, -1)
 
 
 def clip_boxes(boxes_nc4, width, height):
