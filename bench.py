@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--strict-fp32", action="store_true", help="disable TF32 tensor-core math in torch GEMM/conv")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--k-margin", type=float, default=1.5, help="bound on K = margin * largest K seen + 64, on a --k-granule grid")
+    ap.add_argument("--k-granule", type=int, default=128)
     ap.add_argument("--sync-k", action="store_true", help="read K back inside the step (one host sync) instead of speculating")
     ap.add_argument("--profile-range", action="store_true",
                     help="bracket the timed resident steps with cudaProfilerStart/Stop (ncu --profile-from-start off)")
@@ -192,6 +194,7 @@ def run_ours(args):
     # as `found_inf` and skips the update, and the step is redone with the larger bound (exact arithmetic either way).
     evaluator = model.roi_heads.loss_evaluator
     evaluator.speculative_k = not args.sync_k
+    evaluator.k_margin, evaluator.k_granule = args.k_margin, args.k_granule
     overflow_log = []
 
     def step(images_d, props):

@@ -63,6 +63,7 @@ class RoIRegLossComputation(object):
         # (bench.py hands it to the fused optimizer as `found_inf`, which skips the update, and redoes the step).
         self.speculative_k = False
         self.k_margin = 2.0
+        self.k_granule = 256
         self.overflow = None
         self._k_cap = None
         self._k_host = None
@@ -143,7 +144,8 @@ class RoIRegLossComputation(object):
     def _cap_for(self, k):
         """Bound for a batch of k positives: margin, then a coarse grid so the padded shapes (GEMM heuristics, allocator
         blocks) change rarely."""
-        return (int(k * self.k_margin) + 64 + 255) // 256 * 256
+        g = self.k_granule
+        return (int(k * self.k_margin) + 64 + g - 1) // g * g
 
     def _record_k(self, kdev):
         if self._k_host is None:
