@@ -85,8 +85,37 @@ def gen_postprocess():
     print("wrote", path, {k: np.asarray(v).shape for k, v in out.items() if "out" in k})
 
 
+def gen_tta():
+    """N4: the merge of engine/bbox_aug.py (transpose back, resize to the first view, mean) with the reference's BoxList."""
+    ref_shims.install()
+    from wetectron.structures.bounding_box import FLIP_LEFT_RIGHT, BoxList
+    g = torch.Generator().manual_seed(23)
+    n = 120
+    views = [((500, 375), False), ((500, 375), True), ((640, 480), False), ((1000, 750), True), ((864, 600), False)]
+    out, lists = {}, []
+    for v, (size, flip) in enumerate(views):
+        W, H = size
+        x1 = torch.rand(n, generator=g) * (W - 40); y1 = torch.rand(n, generator=g) * (H - 40)
+        b = torch.stack([x1, y1, x1 + 10 + torch.rand(n, generator=g) * 25, y1 + 10 + torch.rand(n, generator=g) * 25], 1)
+        sc = torch.rand(n, generator=g)
+        bl = BoxList(b.clone(), size, "xyxy"); bl.add_field("scores", sc)
+        out["v%d_boxes" % v], out["v%d_scores" % v], out["v%d_size" % v], out["v%d_flip" % v] = b.numpy(), sc.numpy(), np.array(size), flip
+        if flip:
+            bl = bl.transpose(FLIP_LEFT_RIGHT)
+        lists.append(bl if v == 0 else bl.resize(lists[0].size))
+    out["avg_boxes"] = torch.mean(torch.stack([b.bbox for b in lists]), dim=0).numpy()
+    out["avg_scores"] = torch.mean(torch.stack([b.get_field("scores") for b in lists]), dim=0).numpy()
+    out["union_boxes"] = torch.cat([b.bbox for b in lists]).numpy()
+    out["n_views"] = len(views)
+    path = os.path.join(ROOT, "tests", "golden", "tta_merge.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path)
+
+
 if __name__ == "__main__":
-    if "--postprocess" in sys.argv:
+    if "--tta" in sys.argv:
+        gen_tta()
+    elif "--postprocess" in sys.argv:
         gen_postprocess()
     else:
         main()

@@ -73,3 +73,50 @@ def test_model_eval_returns_detections():
         assert bool((lab[1:] >= lab[:-1]).all())
         same = lab[1:] == lab[:-1]
         assert bool((sc[1:][same] <= sc[:-1][same]).all())
+
+
+def test_tta_merge_matches_reference(golden):
+    """engine/bbox_aug.py merge: mirror back, resize to the first view's frame, AVG / UNION -- bit-exact against the
+    reference's BoxList.transpose / resize / torch.mean (oracle/gen_golden_data.py --tta)."""
+    from odwscl_b200 import bbox_aug
+    from odwscl_b200.structures import BoxList
+    G = golden("tta_merge.npz")
+    lists = []
+    for v in range(int(G["n_views"])):
+        bl = BoxList(torch.from_numpy(G["v%d_boxes" % v]), tuple(int(x) for x in G["v%d_size" % v]), "xyxy")
+        bl.add_field("scores", torch.from_numpy(G["v%d_scores" % v]))
+        first = lists[0].size if lists else bl.size
+        lists.append(bbox_aug.to_first_frame(bl, bool(G["v%d_flip" % v]), first))
+    avg = bbox_aug.merge_views(lists, "AVG")
+    assert np.array_equal(avg.bbox.numpy(), G["avg_boxes"]) and np.array_equal(avg.get_field("scores").numpy(), G["avg_scores"])
+    assert np.array_equal(bbox_aug.merge_views(lists, "UNION").bbox.numpy(), G["union_boxes"])
+    with pytest.raises(ValueError):
+        bbox_aug.merge_views(lists, "MAX")
+
+
+@pytest.mark.gpu
+def test_tta_loop_end_to_end():
+    """Three views (identity, mirrored, rescaled) through the eval-mode detector, merged and filtered once."""
+    from odwscl_b200 import bbox_aug, data
+    from odwscl_b200.config import cfg
+    from odwscl_b200.modeling import build_detection_model
+    from odwscl_b200.structures import BoxList
+    from odwscl_b200.synth import synth_batch
+    torch.manual_seed(0)
+    model = build_detection_model(cfg).cuda().eval()
+    model.roi_heads.strong_post_processor.bbox_aug_enabled = True
+    images, _, boxes, _ = synth_batch(1, 200, 400, 320, seed=9)
+    W, H = 400, 320
+    img = images[:, :, :H, :W]
+    views = [{"images": images.cuda(), "rois": [BoxList(boxes[0].cuda(), (W, H), "xyxy")], "hflip": False},
+             {"images": images.flip(3).cuda() if images.shape[3] == W else torch.nn.functional.pad(img.flip(3), (0, images.shape[3] - W)).cuda(),
+              "rois": [BoxList(data.hflip_boxes(boxes[0], W).cuda(), (W, H), "xyxy")], "hflip": True}]
+    big = torch.nn.functional.interpolate(img, size=(480, 600), mode="bilinear", align_corners=False)
+    big_p, _ = data.to_image_list([big[0]], 32)
+    views.append({"images": big_p.cuda(), "rois": [BoxList(data.resize_boxes(boxes[0], (W, H), (600, 480)).cuda(), (600, 480), "xyxy")],
+                  "hflip": False})
+    res = bbox_aug.im_detect_bbox_aug(model, views, 21, "AVG")
+    assert len(res) == 1 and 0 < len(res[0]) <= 120
+    r = res[0]
+    assert tuple(r.size) == (W, H) and int(r.get_field("labels").min()) >= 1
+    assert bool(torch.isfinite(r.bbox).all()) and bool(torch.isfinite(r.get_field("scores")).all())
