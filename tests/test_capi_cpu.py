@@ -93,3 +93,22 @@ def test_wetectron_shim_installs_C():
             sys.modules.pop(k, None)
             if v is not None:
                 sys.modules[k] = v
+
+
+def test_speculative_bound_policy():
+    """Host logic of the sync-free step: the bound on K is margin * K + 64 on a grid, never shrinks, and the library
+    default is the conservative one (bench.py tightens it and redoes flagged steps)."""
+    from odwscl_b200.config import cfg
+    from odwscl_b200.modeling.loss import RoIRegLossComputation
+    ev = RoIRegLossComputation(cfg)
+    assert ev.speculative_k is False and (ev.k_margin, ev.k_granule) == (2.0, 256)
+    assert ev._cap_for(0) == 256 and ev._cap_for(300) == 768 and ev._cap_for(96) == 256
+    ev.k_margin, ev.k_granule = 1.5, 128
+    assert ev._cap_for(300) == 640 and ev._cap_for(250) == 512
+    assert ev._poll_k_cap() is None                       # nothing observed yet: the first step reads K back
+
+
+def test_every_counted_entry_point_is_exported():
+    from odwscl_b200 import capi
+    assert set(capi._LAUNCHES) <= set(capi.EXPORTS)
+    assert set(capi._WORK) <= set(capi.EXPORTS)
