@@ -194,6 +194,15 @@ int odwscl_dropblock_rows_f32(const float* x, const float* centres, int R, int C
                               int block, float* y, float* scale_io, int reuse_scale,
                               const int32_t* n_valid_dev, odwscl_stream_t stream);
 
+/* Same over a batch made of P row SEGMENTS (seg_off_dev [P+1] int32, device-resident, ascending; segment p = rows
+ * [seg_off[p], seg_off[p+1])): every segment is renormalised by its own numel/sum -- the arithmetic of the reference's
+ * per-(image, class) drop_pool calls (roi_heads/weak_head/loss.py:299, modeling/backbone/vgg16.py:173-175) in one
+ * launch pair.  Rows >= seg_off[P] are padding and are zero-filled.  scale_seg [P,2] fp32 = (sum, numel/sum) per
+ * segment; reuse_scale != 0 applies the stored scales (the backward). */
+int odwscl_dropblock_seg_f32(const float* x, const float* centres, int R, int C, int ph, int pw, int block,
+                             float* y, const int32_t* seg_off_dev, int P, float* scale_seg, int reuse_scale,
+                             odwscl_stream_t stream);
+
 /* ---- N4 (test time): PostProcessor.filter_results (roi_heads/box_head/inference.py:216-258) -- for every foreground
  * class j in [1,C): candidates with scores[i,j] > score_thr, torchvision-semantics NMS at `thr` on boxes[i, 4j..4j+3],
  * all classes in ONE launch (one CTA per class, sort + sweep in shared memory, no host round trip).  boxes [N,C*4],

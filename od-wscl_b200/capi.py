@@ -25,7 +25,7 @@ _LAUNCHES = {
     "odwscl_roi_align_bwd_f32": 1, "odwscl_box_iou_f32": 1, "odwscl_nms_f32": 1, "odwscl_nms_legacy_f32": 1,
     "odwscl_discover_phase_a_f32": 2, "odwscl_discover_phase_b_f32": 2, "odwscl_bank_assemble": 1,
     "odwscl_supcon_fwd_f32": 2, "odwscl_supcon_bwd_f32": 1, "odwscl_od_layer_f32": 1,
-    "odwscl_dropblock_f32": 3, "odwscl_dropblock_rows_f32": 3, "odwscl_dropblock_mask_f32": 1, "odwscl_sim_nxn_f32": 2, "odwscl_gemm_nt_tf32": 1,
+    "odwscl_dropblock_f32": 3, "odwscl_dropblock_rows_f32": 3, "odwscl_dropblock_seg_f32": 2, "odwscl_dropblock_mask_f32": 1, "odwscl_sim_nxn_f32": 2, "odwscl_gemm_nt_tf32": 1,
     "odwscl_conv3x3_nhwc_tf32": 1, "odwscl_conv3x3_wgrad_nhwc_tf32": 2, "odwscl_conv3x3_c3_f32": 1, "odwscl_maxpool2x2_nhwc_f32": 1,
     "odwscl_maxpool2x2_nhwc_bwd_f32": 1, "odwscl_split_tf32": 1,
     "odwscl_relu_dropout_fwd_f32": 1, "odwscl_relu_dropout_bwd_f32": 1, "odwscl_conv_weight_xform_f32": 1,
@@ -54,6 +54,7 @@ _SIGS = {
     "odwscl_od_layer_f32": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _I, _P, _P, _F, _P, _P, _P, _P]),
     "odwscl_dropblock_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P]),
     "odwscl_dropblock_rows_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P]),
+    "odwscl_dropblock_seg_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _I, _P]),
     "odwscl_sim_nxn_ws_bytes": (_Z, [_I]),
     "odwscl_sim_nxn_f32": (_I, [_P, _I, _P, _P, _Z, _P]),
     "odwscl_gemm_nt_tf32": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
@@ -345,6 +346,23 @@ def dropblock(x, centres, block, scale_io=None, n_valid=None, out=None):
             _call("odwscl_dropblock_rows_f32", _ptr(x), _ptr(centres), R, C, ph, pw, int(block), _ptr(y),
                   _ptr(scale_io), int(reuse), _ptr(_chk(n_valid, torch.int32, "n_valid")), _stream())
     return y, scale_io
+
+
+def dropblock_seg(x, centres, block, seg_off, P, scale_seg=None):
+    """DropBlock over a batch of P row segments (seg_off int32 [>=P+1], device), each renormalised on its own (the
+    reference's per-(image, class) drop_pool calls, loss.py:299); rows >= seg_off[P] are padding (zero-filled)."""
+    x, centres = _chk(x, torch.float32, "x"), _chk(centres, torch.float32, "centres")
+    seg_off = _chk(seg_off, torch.int32, "seg_off")
+    assert seg_off.numel() >= P + 1 and P > 0
+    R, C, ph, pw = x.shape
+    y = torch.empty_like(x)
+    reuse = scale_seg is not None
+    if scale_seg is None:
+        scale_seg = torch.empty((P, 2), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _call("odwscl_dropblock_seg_f32", _ptr(x), _ptr(centres), R, C, ph, pw, int(block), _ptr(y), _ptr(seg_off), int(P),
+              _ptr(scale_seg), int(reuse), _stream())
+    return y, scale_seg
 
 
 # ---------------------------------------------------------------- conv stack (NHWC)

@@ -20,7 +20,7 @@ namespace {
 
 using odw::kCtaThreads;
 constexpr int kD = ODWSCL_SIM_DIM;
-constexpr int kMaxPairs = 128;
+constexpr int kMaxPairs = 256;   // (image, positive class) pairs per call: 8 images x 32 classes
 
 // block-wide first-max argmax: larger value wins, ties go to the smaller index (torch.argmax /
 // numpy argmax on the CPU reference).  s_v / s_i: 32 entries each.
@@ -162,7 +162,7 @@ phase_a_rows_kernel(const int32_t* __restrict__ img_off, int C, const float* __r
 // ------------------------------------------------------------------------------ phase B
 struct PhaseBSmem {
   float* fq;            // [128] query embedding
-  float* sim;           // [Ncap]
+  float* sim;           // [Ncap]  (aliases key: the similarity row is dead once `close` is decided)
   uint8_t* close;       // [Ncap]
   float* key;           // [L]
   int* id;              // [L]
@@ -175,8 +175,8 @@ __device__ __forceinline__ PhaseBSmem carve_b(unsigned char* smem, int Ncap, int
   PhaseBSmem s;
   s.box = reinterpret_cast<float4*>(smem);
   s.fq = reinterpret_cast<float*>(s.box + L);
-  s.sim = s.fq + kD;
-  s.key = s.sim + Ncap;
+  s.key = s.fq + kD;
+  s.sim = s.key;                                   // L >= Ncap
   s.id = reinterpret_cast<int*>(s.key + L);
   s.scan = s.id + L;
   s.close = reinterpret_cast<uint8_t*>(s.scan + 64);
@@ -184,7 +184,7 @@ __device__ __forceinline__ PhaseBSmem carve_b(unsigned char* smem, int Ncap, int
   return s;
 }
 static size_t phase_b_smem_bytes(int Ncap, int L) {
-  return (size_t)L * 16 + kD * 4 + (size_t)Ncap * 4 + (size_t)L * 8 + 64 * 4 + (size_t)Ncap + L;
+  return (size_t)L * 16 + kD * 4 + (size_t)L * 8 + 64 * 4 + (size_t)Ncap + L;     // 213.8 KB at Ncap = 8192
 }
 
 // phase_b_select_kernel: grid (P, 3) -- one CTA per (pair, refinement branch).  Everything that is independent of
@@ -330,7 +330,15 @@ phase_b_merge_kernel(const int32_t* __restrict__ img_off, int C, const float* __
 }
 
 // ------------------------------------------------------------------------------ bank assembly
-struct Seg { int src_kind, q, i, dst, len; };   // kind 0: F rows of phase A, 1: drop, 2: noise, 3: phase B
+// kind 0: F rows of phase A, 1: drop, 2: noise, 3: phase B.  Packed (12 bytes) so 2 x 6 x kMaxPairs fit static smem.
+struct Seg {
+  int kqi, dst, len;
+  __device__ Seg() {}
+  __device__ Seg(int kind, int q_, int i_, int dst_, int len_) : kqi(kind | (i_ << 2) | (q_ << 4)), dst(dst_), len(len_) {}
+  __device__ int src_kind() const { return kqi & 3; }
+  __device__ int i() const { return (kqi >> 2) & 3; }
+  __device__ int q() const { return kqi >> 4; }
+};
 
 __global__ void __launch_bounds__(kCtaThreads, 1)
 bank_assemble_kernel(const int32_t* __restrict__ pair_img, const int32_t* __restrict__ pair_cls, int P, int B,
@@ -350,20 +358,20 @@ bank_assemble_kernel(const int32_t* __restrict__ pair_img, const int32_t* __rest
       for (int q = 0; q < P; ++q) {
         if (pair_cls[q] != c) continue;
         const int len = offA[q + 1] - offA[q];
-        for (int k = 0; k < 3; ++k) { s_bank[nb++] = Seg{k, q, 0, dst, len}; dst += len; }
+        for (int k = 0; k < 3; ++k) { s_bank[nb++] = Seg(k, q, 0, dst, len); dst += len; }
       }
       for (int q = 0; q < P; ++q) {
         if (pair_cls[q] != c) continue;
         for (int i = 0; i < 3; ++i) {
           const int len = new_cnt[q * 3 + i];
-          s_bank[nb++] = Seg{3, q, i, dst, len}; dst += len;
+          s_bank[nb++] = Seg(3, q, i, dst, len); dst += len;
         }
       }
     }
     int nw = 0, wd = 0;
     for (int q = 0; q < P; ++q) {                         // execution-order weights (loss.py:296-305)
       const int len = offA[q + 1] - offA[q];
-      for (int k = 0; k < 3; ++k) { s_w[nw++] = Seg{k, q, 0, wd, len}; wd += len; }
+      for (int k = 0; k < 3; ++k) { s_w[nw++] = Seg(k, q, 0, wd, len); wd += len; }
     }
     int q0 = 0;
     while (q0 < P) {                                      // loss.py:311-345: image, branch, class
@@ -372,7 +380,7 @@ bank_assemble_kernel(const int32_t* __restrict__ pair_img, const int32_t* __rest
       for (int i = 0; i < 3; ++i)
         for (int q = q0; q < q1; ++q) {
           const int len = new_cnt[q * 3 + i];
-          s_w[nw++] = Seg{3, q, i, wd, len}; wd += len;
+          s_w[nw++] = Seg(3, q, i, wd, len); wd += len;
         }
       q0 = q1;
     }
@@ -383,24 +391,26 @@ bank_assemble_kernel(const int32_t* __restrict__ pair_img, const int32_t* __rest
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int sidx = wid; sidx < s_nb; sidx += nwarps) {
     const Seg g = s_bank[sidx];
-    const int cls = pair_cls[g.q];
-    const int off = img_off[pair_img[g.q]];
+    const int gq = g.q(), gi = g.i(), kind = g.src_kind();
+    const int cls = pair_cls[gq];
+    const int off = img_off[pair_img[gq]];
     for (int k = lane; k < g.len; k += 32) {
       if (g.dst + k >= Mcap) break;
       int src;
-      if (g.src_kind == 0) src = rowsA[offA[g.q] + k];
-      else if (g.src_kind == 1) src = R + offA[g.q] + k;
-      else if (g.src_kind == 2) src = R + K + offA[g.q] + k;
-      else src = off + newl[(size_t)(g.q * 3 + g.i) * Ncap + k];
+      if (kind == 0) src = rowsA[offA[gq] + k];
+      else if (kind == 1) src = R + offA[gq] + k;
+      else if (kind == 2) src = R + K + offA[gq] + k;
+      else src = off + newl[(size_t)(gq * 3 + gi) * Ncap + k];
       row_src[g.dst + k] = src;
       row_lab[g.dst + k] = cls;
     }
   }
   for (int sidx = wid; sidx < s_nw; sidx += nwarps) {
     const Seg g = s_w[sidx];
+    const int gq = g.q(), gi = g.i(), kind = g.src_kind();
     for (int k = lane; k < g.len; k += 32) {
       if (g.dst + k >= Mcap) break;
-      row_w[g.dst + k] = g.src_kind < 3 ? hardA[offA[g.q] + k] : hardB[(size_t)(g.q * 3 + g.i) * Ncap + k];
+      row_w[g.dst + k] = kind < 3 ? hardA[offA[gq] + k] : hardB[(size_t)(gq * 3 + gi) * Ncap + k];
     }
   }
 }

@@ -25,6 +25,24 @@ class _DropBlockFn(Function):
         return gx, None, None, None
 
 
+class _DropBlockSegFn(Function):
+    """DropBlock over P row segments with one renormalisation per segment (csrc/dropblock.cu, segmented variant)."""
+
+    @staticmethod
+    def forward(ctx, x, centres, block, seg_off, P):
+        y, scale_seg = capi.dropblock_seg(x, centres, block, seg_off, P)
+        ctx.save_for_backward(centres, seg_off, scale_seg)
+        ctx.block, ctx.P = block, P
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        centres, seg_off, scale_seg = ctx.saved_tensors
+        gx, _ = capi.dropblock_seg(gy.contiguous(), centres, ctx.block, seg_off, ctx.P, scale_seg)
+        return gx, None, None, None, None
+
+
 class DropBlock2D(nn.Module):
     def __init__(self, drop_prob, block_size):
         super().__init__()
@@ -32,8 +50,10 @@ class DropBlock2D(nn.Module):
         self.block_size = block_size
         self.centre_sampler = None     # test hook: callable(n, h, w, gamma, device) -> float mask
 
-    def forward(self, x, n_valid=None):
-        """`n_valid` (int32 device tensor [1], optional): x is a padded batch whose first n_valid rows are real."""
+    def forward(self, x, n_valid=None, seg_off=None):
+        """`n_valid` (int32 device tensor [1], optional): x is a padded batch whose first n_valid rows are real.
+        `seg_off` (int32 device tensor [P+1], optional): x is a batch of P row segments, each renormalised on its own
+        (= P separate calls of the reference module); rows past seg_off[P] are padding."""
         assert x.dim() == 4, "Expected input with 4 dimensions (bsize, channels, height, width)"
         if not self.training or self.drop_prob == 0.0:
             return x
@@ -45,4 +65,7 @@ class DropBlock2D(nn.Module):
             centres = self.centre_sampler(n, h, w, gamma, x.device)
         else:
             centres = (torch.rand(n, h, w, device=x.device) < gamma).float()   # :42
+        if seg_off is not None:
+            return _DropBlockSegFn.apply(x.contiguous(), centres.contiguous(), self.block_size, seg_off,
+                                         seg_off.numel() - 1)
         return _DropBlockFn.apply(x.contiguous(), centres.contiguous(), self.block_size, n_valid)

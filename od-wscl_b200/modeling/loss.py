@@ -125,6 +125,7 @@ class RoIRegLossComputation(object):
         capi.discover_phase_b(st, Fm.detach(), E.detach(), self.nms)
         Mcap = 3 * K + 3 * sum(sizes[b] for b in pair_img)
         capi.bank_assemble(st, C - 1, Mcap)
+        st.E = E.detach()                       # [2K,128] augmented-positive embeddings (drop rows, then noise rows)
         self.last_state = st
         losses["loss_sim"] = self.sim_lmda * supcon_bank_loss(Fm, E, st.row_src, st.row_lab, st.row_w, st.M, Mcap,
                                                               self.temp)               # loss.py:347
@@ -165,11 +166,15 @@ class RoIRegLossComputation(object):
         rows = st.rowsA[:K].long()
         if self.batch_aug:
             X = _gather(clean_pooled_feats, rows)
-            aug = torch.cat([feature_extractor.drop_pool(X), feature_extractor.noise_pool(X)], dim=0)
+            feature_extractor._aug_rows = rows                   # test hook: row-keyed replay of the stochastic layers
+            # one launch over all (image, class) groups; DropBlock renormalises each group on its own (loss.py:299)
+            aug = torch.cat([feature_extractor.drop_pool(X, seg_off=st.offA), feature_extractor.noise_pool(X)], dim=0)
         else:
             drops, noises = [], []
             for p in range(P):
-                Xp = _gather(clean_pooled_feats, rows[int(offA_h[p]):int(offA_h[p + 1])])
+                rp = rows[int(offA_h[p]):int(offA_h[p + 1])]
+                Xp = _gather(clean_pooled_feats, rp)
+                feature_extractor._aug_rows = rp
                 drops.append(feature_extractor.drop_pool(Xp))
                 noises.append(feature_extractor.noise_pool(Xp))
             aug = torch.cat(drops + noises, dim=0)
@@ -178,7 +183,7 @@ class RoIRegLossComputation(object):
 
     def _augmented_positives_speculative(self, st, P, Ncap, clean_pooled_feats, feature_extractor, model_sim):
         """Same arithmetic over a batch padded to the bound Kc: rows past the device-resident K are masked (DropBlock
-        renormalises over the first K rows only), and the [2K,128] layout the discovery kernels address (drop rows,
+        renormalises each (image, class) segment of the first K rows on its own), and the [2K,128] layout the discovery kernels address (drop rows,
         then noise rows, stride K) is rebuilt with a gather -- nothing is read back."""
         dev = st.offA.device
         Kc = min(self._k_cap, P * Ncap)
@@ -188,7 +193,8 @@ class RoIRegLossComputation(object):
         ar = torch.arange(Kc, device=dev)
         rows = torch.where(ar < kv, st.rowsA[:Kc].long(), torch.zeros_like(ar))
         X = _gather(clean_pooled_feats, rows)
-        aug = torch.cat([feature_extractor.drop_pool(X, n_valid=kdev), feature_extractor.noise_pool(X)], dim=0)
+        feature_extractor._aug_rows = rows
+        aug = torch.cat([feature_extractor.drop_pool(X, seg_off=st.offA), feature_extractor.noise_pool(X)], dim=0)
         Epad = model_sim(feature_extractor.forward_neck(aug))     # [2Kc,128]
         j = torch.arange(2 * P * Ncap, device=dev)                # K <= P*Ncap always: every address the kernels form is in range
         jj = j - k64

@@ -217,7 +217,11 @@ class VGG16FC67ROIFeatureExtractor(nn.Module):
     def forward_dropblock(self, pooled_feats, proposals):  # vgg16.py:165-167
         return self.dropblock(pooled_feats)
 
-    def drop_pool(self, pooled_feats, n_valid=None):     # vgg16.py:173-175
+    def drop_pool(self, pooled_feats, n_valid=None, seg_off=None):     # vgg16.py:173-175
+        """`seg_off`: the batch holds several (image, class) groups of positives; each is renormalised on its own, as
+        the reference's one-call-per-group loop does (loss.py:299)."""
+        if seg_off is not None:
+            return self.sim_drop(pooled_feats, seg_off=seg_off)
         return self.sim_drop(pooled_feats, n_valid) if n_valid is not None else self.sim_drop(pooled_feats)
 
     def noise_pool(self, pooled_feats):                  # vgg16.py:177-180

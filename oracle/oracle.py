@@ -464,17 +464,31 @@ def model_forward(sd: Dict[str, torch.Tensor], images: torch.Tensor, boxes: List
     bbs = [lin("bbox_pred1"), lin("bbox_pred2"), lin("bbox_pred3")]
     sizes = [b.shape[0] for b in boxes]
     pooled_l = pooled.split(sizes)
+    img_off = [0]
+    for n in sizes:
+        img_off.append(img_off[-1] + n)
+    keyed = hasattr(rng, "noise_rows")        # row-keyed source: draws depend on the proposal's global row id only
+    emb_log = {}
 
     def embed_aug(b, c, I, kind):
         x = pooled_l[b][I]
         if kind == "drop":                                                 # vgg16.py:173-175
-            x = dropblock(x, rng.dropblock_centres(x.shape[0], 1), 1)
+            cen = rng.dropblock_centres_rows(I + img_off[b], 1) if keyed else rng.dropblock_centres(x.shape[0], 1)
+            x = dropblock(x, cen, 1)
         else:                                                              # vgg16.py:177-180
-            x = rng.noise(x.shape) * x + x
-        return sim_net(neck(x))
+            nz = rng.noise_rows(I + img_off[b], x.shape) if keyed else rng.noise(x.shape)
+            x = nz * x + x
+        e = sim_net(neck(x))
+        emb_log[(b, c, kind)] = e.detach()
+        return e
 
-    return roi_reg_loss(cls, det, refs, bbs, simf, boxes, labels_per_img, embed_aug,
-                        thres=thres, nms=nms, lmda=lmda, temp=temp, return_trace=return_trace)
+    out = roi_reg_loss(cls, det, refs, bbs, simf, boxes, labels_per_img, embed_aug,
+                       thres=thres, nms=nms, lmda=lmda, temp=temp, return_trace=return_trace)
+    if return_trace:
+        out[1].update(feat=feat.detach(), pooled=pooled.detach(), simf=simf.detach(), cls=cls.detach(), det=det.detach(),
+                      refs=[r.detach() for r in refs], bbs=[r.detach() for r in bbs], emb=emb_log,
+                      clean=clean.detach(), aug=aug.detach())
+    return out
 
 
 class StochasticSource:

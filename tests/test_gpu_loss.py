@@ -99,14 +99,20 @@ def test_roi_reg_loss_golden(golden, tag):
                                    err_msg=k)
 
 
-def test_discovery_stagewise_vs_oracle_random():
-    """Larger random case on the exact similarity grid (N = 1500 / 1100, 3 + 2 classes): every
-    discovered set, bank row order and weight order equals the oracle's, bit for bit."""
+@pytest.mark.parametrize("sizes,pos", [
+    ([1500, 1100], [[2, 9, 17], [5, 9]]),
+    ([8192], [[3, 11]]),                                        # the largest proposal list the C ABI accepts (smem carve)
+    ([40] * 30, [[c % 20 for c in range(b, b + 5)] for b in range(30)]),   # 150 pairs (> 128), many small images
+])
+def test_discovery_stagewise_vs_oracle_random(sizes, pos):
+    """Larger random cases on the exact similarity grid (N = 1500 / 1100 with 3 + 2 classes; one image at the
+    Ncap = 8192 limit; 150 (image, class) pairs): every discovered set, bank row order and weight order equals the
+    oracle's, bit for bit."""
     from odwscl_b200 import capi
     from oracle.gen_golden import grid_features
     g = torch.Generator().manual_seed(21)
-    sizes, C = [1500, 1100], 21
-    pos = [[2, 9, 17], [5, 9]]
+    C = 21
+    pos = [sorted(set(p)) for p in pos]
     R = sum(sizes)
     boxes = [orc.synth_boxes(n, 1000, 600, g) for n in sizes]
     mk = lambda *s: torch.randn(*s, generator=g) * 2.0
@@ -127,18 +133,20 @@ def test_discovery_stagewise_vs_oracle_random():
             ofeat.append(torch.cat(rows)); olab += [c] * ofeat[-1].shape[0]
     ofeat, ow = torch.cat(ofeat), torch.cat([w.view(-1) for w in Wt])
 
-    pair_img = [b for b in range(2) for _ in pos[b]]
-    pair_cls = [c for b in range(2) for c in pos[b]]
+    pair_img = [b for b in range(len(sizes)) for _ in pos[b]]
+    pair_cls = [c for b in range(len(sizes)) for c in pos[b]]
     P = len(pair_img)
     i32 = lambda x: torch.tensor(x, dtype=torch.int32).cuda()
+    img_off = [0]
+    for n_ in sizes:
+        img_off.append(img_off[-1] + n_)
     scores = (final.cuda().contiguous(), torch.softmax(refl[0], 1).cuda().contiguous(),
               torch.softmax(refl[1], 1).cuda().contiguous())
-    st = capi.discover_phase_a(torch.cat(boxes).cuda(), i32([0, sizes[0], R]), scores, i32(pair_img), i32(pair_cls),
+    st = capi.discover_phase_a(torch.cat(boxes).cuda(), i32(img_off), scores, i32(pair_img), i32(pair_cls),
                                max(sizes), 0.5)
     offA = st.offA.cpu().numpy()
     K = int(offA[P])
     rowsA = st.rowsA[:K].cpu().numpy()
-    img_off = [0, sizes[0]]
     for p in range(P):
         exp = tr["phaseA_idx"][(pair_img[p], pair_cls[p])] + img_off[pair_img[p]]
         assert np.array_equal(rowsA[offA[p]:offA[p + 1]], exp)
