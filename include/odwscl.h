@@ -176,6 +176,38 @@ int odwscl_relu_dropout_bwd_f32(const float* y, const float* gy, float* gx, long
 int odwscl_conv_weight_xform_f32(const float* w_oihw, int Cout, int Cin, float* w_krsc, float* w_crsk_flip,
                                  int round_tf32, odwscl_stream_t stream);
 
+/* ---- A6 / A7 / N1: the fully-connected block -- fc6 + fc7 (modeling/backbone/vgg16.py:122-130,148-162), Sim_Net
+ * (roi_heads/sim_head/sim_net.py:10-26) and the MIST predictor heads (roi_heads/weak_head/roi_weak_predictors.py:
+ * 158-165); replaces the cuBLAS GEMMs behind nn.Linear forward / backward plus the separate ReLU, Dropout and
+ * gradient-accumulation kernels.  One persistent CTA-pair tcgen05 kernel (TF32 math, fp32 accumulate in TMEM):
+ *     C[M,N] (+)= sum_k A(m,k) * B(n,k)
+ * A is [M,K] row-major (a_mn_major = 0, pitch lda) or [K,M] row-major (a_mn_major = 1); B is [N,K] (b_mn_major = 0,
+ * pitch ldb) or [K,N] (b_mn_major = 1) -- so forward (X W^T), input gradient (dY W) and weight gradient (dY^T X)
+ * all read the tensors where they lie.  Pitches in floats, multiples of 4; A, B, C, mask_src 16-byte aligned.
+ * flags (fused epilogue, applied in this order):
+ *   ODWSCL_FC_BIAS     + bias[n]
+ *   ODWSCL_FC_ACCUM    + the previous content of C (3xTF32 passes; folding a second weight gradient, beta = 1)
+ *   ODWSCL_FC_RELU     max(., 0)
+ *   ODWSCL_FC_DROPOUT  nn.Dropout(dropout_p): Philox4x32-10 keyed by (seed, row * N + col); survivors x 1/(1-p)
+ *   ODWSCL_FC_MASK     x mask_scale where mask_src[m, n] > 0, else 0 (the ReLU+Dropout derivative of the layer below:
+ *                      mask_src = its saved output, mask_scale = 1/(1-p))
+ *   ODWSCL_FC_ROUND    round to TF32 (cvt.rna) -- for outputs another tensor-core GEMM consumes
+ * max_pairs > 0 caps the resident CTA pairs (leave SMs to a concurrent NCCL all-reduce); 0 = all 74. */
+#define ODWSCL_FC_BIAS 1
+#define ODWSCL_FC_ACCUM 2
+#define ODWSCL_FC_RELU 4
+#define ODWSCL_FC_DROPOUT 8
+#define ODWSCL_FC_MASK 16
+#define ODWSCL_FC_ROUND 32
+int odwscl_fc_gemm_tf32(const float* A, int lda, int a_mn_major, const float* B, int ldb, int b_mn_major, float* C,
+                        int ldc, int M, int N, int K, int flags, const float* bias, const float* mask_src,
+                        int ld_mask, float mask_scale, float dropout_p, unsigned long long seed, int max_pairs,
+                        odwscl_stream_t stream);
+/* out[c] (+)= sum_r x[r, c] over a [rows, cols] matrix of pitch ld: the bias gradients of the block above
+ * (accumulate != 0 adds to out, which folds a second call's gradient). */
+int odwscl_colsum_f32(const float* x, long long rows, int cols, int ld, float* out, int accumulate,
+                      odwscl_stream_t stream);
+
 /* ---- A15: DropBlock2D apply (modeling/dropblock/drop_block.py:29-66) with a device-sampled
  * centre mask [R,ph,pw] (1.0 = drop centre): block mask by block x block dilation, global
  * renormalisation numel/sum, y = x * mask * scale in ONE pass over x [R,C,ph,pw].

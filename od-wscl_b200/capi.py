@@ -29,6 +29,7 @@ _LAUNCHES = {
     "odwscl_conv3x3_nhwc_tf32": 1, "odwscl_conv3x3_wgrad_nhwc_tf32": 2, "odwscl_conv3x3_c3_f32": 1, "odwscl_maxpool2x2_nhwc_f32": 1,
     "odwscl_maxpool2x2_nhwc_bwd_f32": 1, "odwscl_split_tf32": 1,
     "odwscl_relu_dropout_fwd_f32": 1, "odwscl_relu_dropout_bwd_f32": 1, "odwscl_conv_weight_xform_f32": 1,
+    "odwscl_fc_gemm_tf32": 1, "odwscl_colsum_f32": 1,
 }
 
 _P, _I, _F, _Z = c_void_p, c_int, c_float, c_size_t
@@ -67,6 +68,8 @@ _SIGS = {
     "odwscl_relu_dropout_fwd_f32": (_I, [_P, ctypes.c_longlong, _F, ctypes.c_ulonglong, _P]),
     "odwscl_relu_dropout_bwd_f32": (_I, [_P, _P, _P, ctypes.c_longlong, _F, _P]),
     "odwscl_conv_weight_xform_f32": (_I, [_P, _I, _I, _P, _P, _I, _P]),
+    "odwscl_fc_gemm_tf32": (_I, [_P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P, _I, _F, _F, ctypes.c_ulonglong, _I, _P]),
+    "odwscl_colsum_f32": (_I, [_P, ctypes.c_longlong, _I, _I, _P, _I, _P]),
     "odwscl_version": (_I, []),
     "odwscl_strerror": (ctypes.c_char_p, [_I]),
 }
@@ -121,6 +124,8 @@ _WORK = {
     "odwscl_sim_nxn_f32": lambda a: ("flop", 2.0 * a[1] * a[1] * 128),
     # (A, B, C, M, N, K, ...)
     "odwscl_gemm_nt_tf32": lambda a: ("flop", 2.0 * a[3] * a[4] * a[5]),
+    # (A, lda, a_mn, B, ldb, b_mn, C, ldc, M, N, K, ...)
+    "odwscl_fc_gemm_tf32": lambda a: ("flop", 2.0 * a[8] * a[9] * a[10]),
 }
 
 
@@ -474,6 +479,93 @@ def relu_dropout_backward(y, gy, p):
     with torch.cuda.device(y.device):
         _call("odwscl_relu_dropout_bwd_f32", _ptr(y), _ptr(gy), _ptr(gx), y.numel(), float(p), _stream())
     return gx
+
+
+# ---------------------------------------------------------------- fully-connected block (csrc/fc_gemm.cu)
+FC_BIAS, FC_ACCUM, FC_RELU, FC_DROPOUT, FC_MASK, FC_ROUND = 1, 2, 4, 8, 16, 32
+FC_MAX_PAIRS = 0           # > 0: cap on resident CTA pairs of the fc GEMMs (sharding.py sets it when NCCL shares the SMs)
+
+
+def _rows2d(t, name):
+    """(t', pitch): a 2-D fp32 CUDA tensor with contiguous, 16-byte aligned rows and a pitch (floats) that is a multiple
+    of 4 -- what a TMA descriptor needs.  Tensors that already qualify (incl. row / column slices) are used where they
+    lie; anything else is copied once into a pitch-padded buffer."""
+    if not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor (the fc block has no CPU implementation)" % name)
+    if t.dtype != torch.float32 or t.dim() != 2:
+        raise RuntimeError("%s must be a 2-D float32 tensor" % name)
+    rows, cols = t.shape
+    unit = cols <= 1 or t.stride(1) == 1
+    if rows <= 1:
+        if unit and t.data_ptr() % 16 == 0:
+            return t, (cols + 3) // 4 * 4
+    elif unit and t.stride(0) % 4 == 0 and t.stride(0) >= cols and t.data_ptr() % 16 == 0:
+        return t, t.stride(0)
+    ld = (cols + 3) // 4 * 4
+    buf = torch.empty((rows, ld), dtype=t.dtype, device=t.device)
+    buf[:, :cols].copy_(t)
+    return buf[:, :cols], ld
+
+
+def fc_gemm(A, B, a_mn=False, b_mn=False, out=None, bias=None, relu=False, dropout_p=0.0, seed=0, mask_src=None,
+            mask_scale=1.0, accumulate=False, round_tf32=False):
+    """C[M,N] (+)= sum_k A(m,k) B(n,k) on the persistent tcgen05 CTA-pair kernel (TF32 math, fp32 accumulate).
+    A: [M,K] (a_mn False) or [K,M] (a_mn True); B: [N,K] (b_mn False) or [K,N] (b_mn True); rows contiguous.
+    Fused epilogue: bias, accumulate, ReLU, Dropout(p, seed), derivative mask (mask_src > 0) * mask_scale, TF32 round."""
+    (A, lda), (B, ldb) = _rows2d(A, "A"), _rows2d(B, "B")
+    K, M = (A.shape[0], A.shape[1]) if a_mn else (A.shape[1], A.shape[0])
+    Kb, N = (B.shape[0], B.shape[1]) if b_mn else (B.shape[1], B.shape[0])
+    if K != Kb:
+        raise RuntimeError("fc_gemm: contraction sizes differ (%d vs %d)" % (K, Kb))
+    if out is None:
+        if accumulate:
+            raise RuntimeError("fc_gemm: accumulate needs `out`")
+        ldc = (N + 3) // 4 * 4
+        out = torch.empty((M, ldc), dtype=torch.float32, device=A.device)[:, :N]
+    if tuple(out.shape) != (M, N) or out.dtype != torch.float32 or (N > 1 and out.stride(1) != 1) or out.data_ptr() & 15 \
+            or (M > 1 and out.stride(0) < N):
+        raise RuntimeError("fc_gemm: `out` must be a [%d,%d] float32 tensor with contiguous, 16-byte aligned rows" % (M, N))
+    flags = 0
+    if bias is not None:
+        bias = _chk(bias, torch.float32, "bias")
+        flags |= FC_BIAS
+    if accumulate:
+        flags |= FC_ACCUM
+    if relu:
+        flags |= FC_RELU
+    if dropout_p > 0.0:
+        flags |= FC_DROPOUT
+    ld_mask = 0
+    if mask_src is not None:
+        mask_src, ld_mask = _rows2d(mask_src, "mask_src")
+        assert tuple(mask_src.shape) == (M, N)
+        flags |= FC_MASK
+    if round_tf32:
+        flags |= FC_ROUND
+    if M == 0 or N == 0:
+        return out
+    if K == 0:
+        if not accumulate:
+            out.zero_()
+        return out
+    ldc = out.stride(0) if M > 1 else max(N, out.stride(0))
+    with torch.cuda.device(A.device):
+        _call("odwscl_fc_gemm_tf32", _ptr(A), int(lda), int(a_mn), _ptr(B), int(ldb), int(b_mn), _ptr(out), int(ldc), M, N,
+              K, flags, _ptr(bias), _ptr(mask_src), int(ld_mask), float(mask_scale), float(dropout_p),
+              ctypes.c_ulonglong(seed & (2 ** 64 - 1)), int(FC_MAX_PAIRS), _stream())
+    return out
+
+
+def colsum(x, out=None, accumulate=False):
+    """out[c] (+)= sum_r x[r, c]."""
+    x, ld = _rows2d(x, "x")
+    rows, cols = x.shape
+    if out is None:
+        out = torch.empty((cols,), dtype=torch.float32, device=x.device)
+        accumulate = False
+    with torch.cuda.device(x.device):
+        _call("odwscl_colsum_f32", _ptr(x), rows, cols, int(ld), _ptr(out), int(accumulate), _stream())
+    return out
 
 
 # ---------------------------------------------------------------- object discovery / SupCon

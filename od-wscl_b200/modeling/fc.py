@@ -1,0 +1,107 @@
+"""The fully-connected block of the path on the hand-written tcgen05 GEMM (csrc/fc_gemm.cu): nn.Linear (+ ReLU
+(+ Dropout)) forward, input gradient and weight gradient of fc6 / fc7 (modeling/backbone/vgg16.py:122-130), Sim_Net
+(roi_heads/sim_head/sim_net.py:10-26) and the MIST predictor heads (roi_heads/weak_head/roi_weak_predictors.py:158-165).
+The nn.Linear modules only hold the parameters (the reference's state-dict keys); no cuBLAS call is left on the path.
+
+  forward   Y = act(X W^T + b)     one launch: bias, ReLU, Dropout (Philox, no mask tensor) and TF32 rounding fused
+  backward  dZ = dY * act'(Y)      one pass (fused into the producing dgrad's epilogue when the producer is ours)
+            dX = dZ W              W read where it lies as an MN-major operand
+            dW = dZ^T X            both operands MN-major straight from the activations; a second (small-batch) call of
+                                   the same layer is folded in with the accumulate epilogue instead of a separate
+                                   gradient + add (the two fc6 calls of a step, weak_head.py:107-112 / loss.py:299-310)
+            db = column sums of dZ
+
+`strict` evaluates every product as a 3xTF32 split (hi*hi + hi*lo + lo*hi: fp32-class accuracy) for the parity tests;
+the default is single-pass TF32, the arithmetic torch 1.7.1 (the reference's pin) runs nn.Linear with on tensor-core GPUs.
+"""
+import os
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from .. import capi
+
+ACT_NONE, ACT_RELU, ACT_RELU_DROPOUT = 0, 1, 2
+_seed_state = {"ctr": 0}
+
+
+def next_dropout_seed():
+    """Philox key of one Dropout call: (process seed, rank, call counter) -- no host RNG round trip, distinct per rank
+    (the reference leaves DDP ranks independently seeded)."""
+    _seed_state["ctr"] += 1
+    rank = int(os.environ.get("RANK", "0"))
+    base = torch.initial_seed() & 0xFFFFFFFFFFFF
+    return (base * 0x9E3779B97F4A7C15 + rank * 0xBF58476D1CE4E5B9 + _seed_state["ctr"] * 0x94D049BB133111EB) & (2 ** 64 - 1)
+
+
+def _gemm(A, B, strict, **kw):
+    """fc_gemm, or its 3-pass hi/lo split: the epilogue's bias joins the first pass, the non-linear part the last."""
+    if not strict:
+        return capi.fc_gemm(A, B, **kw)
+    A2 = A if A.is_contiguous() else A.contiguous()
+    B2 = B if B.is_contiguous() else B.contiguous()
+    Ah, Al = capi.split_tf32(A2)
+    Bh, Bl = capi.split_tf32(B2)
+    a_mn, b_mn = kw.get("a_mn", False), kw.get("b_mn", False)
+    out = capi.fc_gemm(Ah, Bh, a_mn=a_mn, b_mn=b_mn, out=kw.get("out"), bias=kw.get("bias"),
+                       accumulate=kw.get("accumulate", False))
+    capi.fc_gemm(Ah, Bl, a_mn=a_mn, b_mn=b_mn, out=out, accumulate=True)
+    return capi.fc_gemm(Al, Bh, a_mn=a_mn, b_mn=b_mn, out=out, accumulate=True, relu=kw.get("relu", False),
+                        dropout_p=kw.get("dropout_p", 0.0), seed=kw.get("seed", 0), mask_src=kw.get("mask_src"),
+                        mask_scale=kw.get("mask_scale", 1.0))
+
+
+class _LinearFn(Function):
+    """y = act(x W^T + b).  `stash` / `role` fold the weight gradients of two calls of the SAME layer into one tensor:
+    the "small" call's backward (it runs first: its node is younger) only stashes (dZ, x), the "main" call's backward
+    accumulates them into its own dW / db through the GEMM's accumulate epilogue.  If the order is ever the other way
+    round the small call returns its own gradient, so the result never depends on the assumption."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act, p, seed, round_out, strict, stash, role):
+        x2 = x
+        y = _gemm(x2, weight, strict, bias=bias, relu=act != ACT_NONE,
+                  dropout_p=p if act == ACT_RELU_DROPOUT else 0.0, seed=seed, round_tf32=round_out and not strict)
+        ctx.save_for_backward(x2, weight, y if act != ACT_NONE else None)
+        ctx.act, ctx.p, ctx.strict, ctx.stash, ctx.role = act, (p if act == ACT_RELU_DROPOUT else 0.0), strict, stash, role
+        ctx.has_bias = bias is not None
+        if role == "main" and stash is not None:
+            stash["has_main"] = True
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, weight, y = ctx.saved_tensors
+        if ctx.act != ACT_NONE:
+            dz = capi.relu_dropout_backward(y, g, ctx.p)              # dY * [y > 0] / (1 - p)
+        else:
+            dz = g
+        gx = _gemm(dz, weight, ctx.strict, b_mn=True) if ctx.needs_input_grad[0] else None
+        st = ctx.stash
+        need_w = ctx.needs_input_grad[1]
+        if ctx.role == "small" and st is not None and st.get("has_main", False) and not st.get("main_done", False):
+            st.setdefault("pending", []).append((dz, x))
+            return (gx,) + (None,) * 9
+        gw = gb = None
+        if need_w:
+            gw = _gemm(dz, x, ctx.strict, a_mn=True, b_mn=True)
+            if ctx.has_bias:
+                gb = capi.colsum(dz)
+            if ctx.role == "main" and st is not None:
+                for dzs, xs in st.pop("pending", []):
+                    _gemm(dzs, xs, ctx.strict, a_mn=True, b_mn=True, out=gw, accumulate=True)
+                    if gb is not None:
+                        capi.colsum(dzs, out=gb, accumulate=True)
+                st["main_done"] = True
+        return (gx, gw, gb) + (None,) * 7
+
+
+def linear(x, weight, bias=None, act=ACT_NONE, p=0.0, seed=0, round_out=False, strict=False, stash=None, role=None):
+    """act(x @ weight.T + bias) on the sm_100a fc kernel.  CUDA fp32 only: there is no CPU / library fallback."""
+    if not x.is_cuda:
+        raise RuntimeError("the fully-connected block has no CPU implementation (sm_100a kernels only)")
+    if x.dim() != 2:
+        x = x.reshape(x.shape[0], -1)
+    return _LinearFn.apply(x.float(), weight, bias, int(act), float(p), int(seed), bool(round_out), bool(strict), stash, role)

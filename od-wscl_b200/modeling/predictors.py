@@ -1,6 +1,6 @@
 """MISTPredictor (roi_heads/weak_head/roi_weak_predictors.py:112-187): 8 linear heads.  State-dict
 keys roi_heads.predictor.{cls_score,det_score,ref1..3,bbox_pred1..3}.  The eight GEMMs over the same
-[R,4096] input are issued as ONE GEMM against the row-concatenated weights (views into the
+[R,4096] input are issued as ONE launch of the tcgen05 fc kernel (csrc/fc_gemm.cu) against the row-concatenated weights (views into the
 per-head parameters are rebuilt each call, so autograd and the state dict are unchanged)."""
 import torch
 import torch.nn as nn
@@ -23,6 +23,7 @@ class MISTPredictor(nn.Module):
         self.bbox_pred2 = nn.Linear(in_channels, nreg * 4)
         self.ref3 = nn.Linear(in_channels, nc)
         self.bbox_pred3 = nn.Linear(in_channels, nreg * 4)
+        self.strict_fp32 = False       # True: 3xTF32 split products (parity tests)
         for m in self.modules():
             if isinstance(m, nn.Linear):
                 nn.init.normal_(m.weight, mean=0, std=0.001)
@@ -34,7 +35,8 @@ class MISTPredictor(nn.Module):
                  self.ref3, self.bbox_pred3]
         W = torch.cat([h.weight for h in heads], 0)
         b = torch.cat([h.bias for h in heads], 0)
-        out = F.linear(x, W, b).split([h.out_features for h in heads], dim=1)
+        from . import fc
+        out = fc.linear(x, W, b, strict=self.strict_fp32).split([h.out_features for h in heads], dim=1)
         cls_logit, det_logit, ref1, bb1, ref2, bb2, ref3, bb3 = out
         if not self.training:
             cls_logit = F.softmax(cls_logit, dim=1)

@@ -20,8 +20,13 @@ class Sim_Net(nn.Module):
                 nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
                 nn.init.constant_(m.bias, 0)
 
+        self.strict_fp32 = False       # True: 3xTF32 split products (parity tests)
+
     def forward(self, roi_feat):
-        return F.normalize(self.mlp(roi_feat), dim=1)
+        from . import fc
+        h = fc.linear(roi_feat, self.mlp[0].weight, self.mlp[0].bias, act=fc.ACT_RELU, round_out=True,
+                      strict=self.strict_fp32)
+        return F.normalize(fc.linear(h, self.mlp[2].weight, self.mlp[2].bias, strict=self.strict_fp32), dim=1)
 
 
 class _SupConBankFn(Function):

@@ -12,60 +12,6 @@ from .dropblock import DropBlock2D
 from .poolers import Pooler
 
 
-class _ReluDropoutFn(torch.autograd.Function):
-    """nn.ReLU(True) + nn.Dropout(p) (vgg16.py:124-125,128-129) as one in-place pass (csrc/elementwise.cu)."""
-
-    @staticmethod
-    def forward(ctx, x, p, seed):
-        from .. import capi
-        y = capi.relu_dropout_(x, p, seed)
-        ctx.mark_dirty(x)
-        ctx.save_for_backward(y)
-        ctx.p = p
-        return y
-
-    @staticmethod
-    def backward(ctx, gy):
-        from .. import capi
-        (y,) = ctx.saved_tensors
-        return capi.relu_dropout_backward(y, gy.contiguous(), ctx.p), None, None
-
-
-class _Fc6Fn(torch.autograd.Function):
-    """fc6 (classifier.1, [4096,25088] = 411 MB) is applied twice per step: to the [2R,25088] clean+augmented batch and to
-    the few augmented positives of the contrastive branch (weak_head.py:107-112, loss.py:299-310).  Autograd would write
-    the second weight gradient as one more 411 MB tensor and add the two (a 1.2 GB pass).  Here the small call's backward
-    (which runs first: its node is younger) only stashes (grad_out, input); the batch call's backward folds it into its
-    own weight gradient with a beta = 1 GEMM.  If the order is ever the other way round the small call falls back to
-    returning its own gradient, so the result never depends on the assumption."""
-
-    @staticmethod
-    def forward(ctx, x, weight, bias, stash, role):
-        ctx.save_for_backward(x, weight)
-        ctx.stash, ctx.role = stash, role
-        if role == "main":
-            stash["has_main"] = True            # a batch call whose backward will collect the stashed gradients exists
-        return torch.nn.functional.linear(x, weight, bias)
-
-    @staticmethod
-    def backward(ctx, g):
-        x, weight = ctx.saved_tensors
-        g = g.contiguous()
-        gx = g @ weight if ctx.needs_input_grad[0] else None
-        st = ctx.stash
-        if ctx.role == "small" and st.get("has_main", False) and not st.get("main_done", False):
-            st.setdefault("pending", []).append((g, x))
-            return gx, None, None, None, None
-        gw = g.t() @ x
-        gb = g.sum(0)
-        if ctx.role == "main":
-            for gs, xs in st.pop("pending", []):
-                gw.addmm_(gs.t(), xs)
-                gb = gb + gs.sum(0)
-            st["main_done"] = True
-        return gx, gw, gb, None, None
-
-
 class Identity(nn.Module):
     def __init__(self, *args, **kwargs):
         super().__init__()
@@ -144,7 +90,7 @@ class VGG16FC67ROIFeatureExtractor(nn.Module):
             self.dropblock = DropBlock2D(block_size=3, drop_prob=0.3)
         self.sim_drop = DropBlock2D(block_size=1, drop_prob=0.3)
         self.noise_sampler = None      # test hook: callable(shape, device) -> N(0,1) tensor
-        self.fuse_relu_dropout = True  # train: ReLU + Dropout of fc6 / fc7 as one in-place kernel
+        self.strict_fp32 = False       # True: every fc product as a 3xTF32 split (parity tests)
         self.merge_fc6_wgrad = True    # train: the two fc6 weight gradients of a step leave as one tensor (_Fc6Fn)
         self._fc6_stash = None
         self.fuse_clean_aug = True     # train: ROIPool + DropBlock into one [2R,...] batch, fc6/fc7 once
@@ -155,22 +101,20 @@ class VGG16FC67ROIFeatureExtractor(nn.Module):
                     nn.init.constant_(m.bias, 0)
 
     def run_classifier(self, x, role=None):
-        """self.classifier(x) (vgg16.py:122-130).  In training on the GPU the two ReLU + Dropout pairs run as one fused
-        in-place kernel each; the Linear layers stay with cuBLAS.  Same parameters, same state-dict keys.  `role`
-        ("main" / "small") routes fc6 through _Fc6Fn so its two weight gradients of a step are produced as one."""
+        """self.classifier(x) (vgg16.py:122-130): Linear + ReLU + Dropout twice, each as ONE launch of the tcgen05 fc
+        kernel (csrc/fc_gemm.cu) with bias, ReLU, Philox Dropout and TF32 rounding fused into its epilogue.  Same
+        parameters, same state-dict keys.  `role` ("main" / "small") marks the two fc6 calls of a training step so their
+        weight gradients leave as one tensor (fc._LinearFn)."""
+        from . import fc
         c = self.classifier
-        if not (self.training and self.fuse_relu_dropout and x.is_cuda and x.dtype == torch.float32):
-            return c(x)
+        stash = self._fc6_stash if (role is not None and self.merge_fc6_wgrad) else None
         for lin, drop in ((c[1], c[3]), (c[4], c[6])):
-            if lin is c[1] and role is not None and self._fc6_stash is not None and lin.weight.requires_grad:
-                x = _Fc6Fn.apply(x, lin.weight, lin.bias, self._fc6_stash, role)
-            else:
-                x = torch.nn.functional.linear(x, lin.weight, lin.bias)
-            if x.numel() % 4 == 0 and x.numel() > 0:
-                seed = int(torch.randint(0, 2 ** 62, (1,)).item())       # CPU generator: no device sync
-                x = _ReluDropoutFn.apply(x, float(drop.p), seed)
-            else:
-                x = drop(torch.relu(x))
+            p = float(drop.p) if self.training else 0.0
+            act = fc.ACT_RELU_DROPOUT if p > 0.0 else fc.ACT_RELU
+            first = lin is c[1]
+            x = fc.linear(x, lin.weight, lin.bias, act=act, p=p, seed=fc.next_dropout_seed() if p > 0.0 else 0,
+                          round_out=True, strict=self.strict_fp32, stash=stash if first else None,
+                          role=role if (first and stash is not None) else None)
         return x
 
     def forward(self, x, proposals):                     # vgg16.py:148-153
