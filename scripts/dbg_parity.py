@@ -6,6 +6,14 @@ from tests import test_gpu_parity_configs as T
 name = sys.argv[1] if len(sys.argv) > 1 else "cfg1_voc07_bs2_2000"
 mode = sys.argv[2] if len(sys.argv) > 2 else "strict"
 _, _, boxes, labels, ref_losses, tr = T._oracle(name)
+import odwscl_b200.modeling.vgg16 as V
+_orig_neck = V.VGG16FC67ROIFeatureExtractor.forward_neck
+AUG = {}
+def _neck(self, x):
+    AUG["x"] = x.detach().clone()
+    AUG["rows"] = self._aug_rows.detach().clone() if hasattr(self, "_aug_rows") else None
+    return _orig_neck(self, x)
+V.VGG16FC67ROIFeatureExtractor.forward_neck = _neck
 got, cap, ev = T._run_product(name, mode)
 st = ev.last_state
 P = st.P
@@ -43,3 +51,15 @@ for p in range(P):
     cos = lambda a, b: float((a * b).sum(1).mean())
     print("pair", p, "cos(F, E_drop) oracle", cos(Fo, e), "product", cos(Fo, ep), "cos(F,E_noise) oracle",
           cos(Fo, tr["emb"][(int(pi[p]), int(pc[p]), "noise")]), "product", cos(Fo, E[K + offA[p]:K + offA[p + 1]]))
+
+aug = AUG["x"].cpu(); Kp = aug.shape[0] // 2
+print("aug shape", aug.shape, "K", K, "rows equal", torch.equal(AUG["rows"].cpu()[:K], rows))
+dp = aug[:K]; npart = aug[Kp:Kp + K]
+print("product drop part: frac zero bins", float((dp.abs().sum(1) == 0).float().mean()), "noise part ratio stats",
+      float((npart / cap["pooled"].cpu()[rows].clamp(min=1e-6)).std()))
+for p in range(P):
+    r = rows[offA[p]:offA[p + 1]]
+    d = orc.dropblock(tr["pooled"][r], ks.dropblock_centres_rows(r, 1), 1)
+    nz = ks.noise_rows(r, d.shape) * tr["pooled"][r] + tr["pooled"][r]
+    print("pair", p, "max|aug_drop - cpu|", float((dp[offA[p]:offA[p + 1]] - d).abs().max()), "max|aug_noise - cpu|",
+          float((npart[offA[p]:offA[p + 1]] - nz).abs().max()), "scale", float(d.abs().max()))

@@ -82,9 +82,15 @@ def _run_product(name, mode):
         t.add_field("labels", torch.as_tensor(lab))
         targets.append(t)
     cap = {}
+    def _keep_first(key):                   # NB a forward hook that returns a value REPLACES the module's output
+        def hook(m, i, o):
+            if key not in cap:
+                cap[key] = o.detach() if torch.is_tensor(o) else o
+            return None
+        return hook
     hooks = [model.backbone.register_forward_hook(lambda m, i, o: cap.__setitem__("feat", o[0].detach())),
-             model.roi_heads.model_sim.register_forward_hook(lambda m, i, o: cap.setdefault("simf", o.detach())),
-             model.roi_heads.predictor.register_forward_hook(lambda m, i, o: cap.__setitem__("heads", o))]
+             model.roi_heads.model_sim.register_forward_hook(_keep_first("simf")),
+             model.roi_heads.predictor.register_forward_hook(_keep_first("heads"))]
     orig = fe.forward_clean_and_aug
 
     def wrapped(x, proposals):
