@@ -23,6 +23,7 @@ from torch.autograd.function import once_differentiable
 from .. import capi
 
 ACT_NONE, ACT_RELU, ACT_RELU_DROPOUT = 0, 1, 2
+FUSE_ACT_BWD = True        # fold the ReLU/Dropout derivative of a layer into the dgrad epilogue of its (only) consumer
 _seed_state = {"ctr": 0}
 
 
@@ -35,21 +36,36 @@ def next_dropout_seed():
     return (base * 0x9E3779B97F4A7C15 + rank * 0xBF58476D1CE4E5B9 + _seed_state["ctr"] * 0x94D049BB133111EB) & (2 ** 64 - 1)
 
 
+STRICT_K_CHUNK = 2048      # contraction length per TMEM accumulation in strict mode (see _gemm)
+
+
 def _gemm(A, B, strict, **kw):
-    """fc_gemm, or its 3-pass hi/lo split: the epilogue's bias joins the first pass, the non-linear part the last."""
+    """fc_gemm, or its fp32-class form for the parity tests: every product as a 3xTF32 hi/lo split (hi*hi + hi*lo +
+    lo*hi; the dropped lo*lo term is <= 2^-22 relative), and the contraction cut into chunks of STRICT_K_CHUNK whose
+    partial results are added in the epilogue (round-to-nearest fp32) -- the tensor core adds into its TMEM accumulator
+    with truncation, which over K = 25088 terms costs ~1e-5 relative (measured), too much for a 1e-4 end-to-end gate.
+    The bias joins the first launch, the non-linear part of the epilogue the last."""
     if not strict:
         return capi.fc_gemm(A, B, **kw)
-    A2 = A if A.is_contiguous() else A.contiguous()
-    B2 = B if B.is_contiguous() else B.contiguous()
-    Ah, Al = capi.split_tf32(A2)
-    Bh, Bl = capi.split_tf32(B2)
     a_mn, b_mn = kw.get("a_mn", False), kw.get("b_mn", False)
-    out = capi.fc_gemm(Ah, Bh, a_mn=a_mn, b_mn=b_mn, out=kw.get("out"), bias=kw.get("bias"),
-                       accumulate=kw.get("accumulate", False))
-    capi.fc_gemm(Ah, Bl, a_mn=a_mn, b_mn=b_mn, out=out, accumulate=True)
-    return capi.fc_gemm(Al, Bh, a_mn=a_mn, b_mn=b_mn, out=out, accumulate=True, relu=kw.get("relu", False),
-                        dropout_p=kw.get("dropout_p", 0.0), seed=kw.get("seed", 0), mask_src=kw.get("mask_src"),
-                        mask_scale=kw.get("mask_scale", 1.0))
+    Ah, Al = capi.split_tf32(A if A.is_contiguous() else A.contiguous())
+    Bh, Bl = capi.split_tf32(B if B.is_contiguous() else B.contiguous())
+    K = A.shape[0] if a_mn else A.shape[1]
+    out, first = kw.get("out"), True
+    passes = []
+    for k0 in range(0, max(K, 1), STRICT_K_CHUNK):
+        k1 = min(K, k0 + STRICT_K_CHUNK)
+        ka = (lambda t: t[k0:k1]) if a_mn else (lambda t: t[:, k0:k1])
+        kb = (lambda t: t[k0:k1]) if b_mn else (lambda t: t[:, k0:k1])
+        passes += [(ka(Ah), kb(Bh)), (ka(Ah), kb(Bl)), (ka(Al), kb(Bh))]
+    for i, (a, b) in enumerate(passes):
+        last = i == len(passes) - 1
+        extra = dict(relu=kw.get("relu", False), dropout_p=kw.get("dropout_p", 0.0), seed=kw.get("seed", 0),
+                     mask_src=kw.get("mask_src"), mask_scale=kw.get("mask_scale", 1.0)) if last else {}
+        out = capi.fc_gemm(a, b, a_mn=a_mn, b_mn=b_mn, out=out, bias=kw.get("bias") if first else None,
+                           accumulate=kw.get("accumulate", False) if first else True, **extra)
+        first = False
+    return out
 
 
 class _LinearFn(Function):
@@ -59,13 +75,14 @@ class _LinearFn(Function):
     round the small call returns its own gradient, so the result never depends on the assumption."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, act, p, seed, round_out, strict, stash, role):
+    def forward(ctx, x, weight, bias, act, p, seed, round_out, strict, stash, role, in_mask_scale, act_bwd_fused):
         x2 = x
         y = _gemm(x2, weight, strict, bias=bias, relu=act != ACT_NONE,
                   dropout_p=p if act == ACT_RELU_DROPOUT else 0.0, seed=seed, round_tf32=round_out and not strict)
         ctx.save_for_backward(x2, weight, y if act != ACT_NONE else None)
         ctx.act, ctx.p, ctx.strict, ctx.stash, ctx.role = act, (p if act == ACT_RELU_DROPOUT else 0.0), strict, stash, role
         ctx.has_bias = bias is not None
+        ctx.in_mask_scale, ctx.act_bwd_fused = in_mask_scale, act_bwd_fused
         if role == "main" and stash is not None:
             stash["has_main"] = True
         return y
@@ -74,16 +91,21 @@ class _LinearFn(Function):
     @once_differentiable
     def backward(ctx, g):
         x, weight, y = ctx.saved_tensors
-        if ctx.act != ACT_NONE:
+        if ctx.act != ACT_NONE and not ctx.act_bwd_fused:
             dz = capi.relu_dropout_backward(y, g, ctx.p)              # dY * [y > 0] / (1 - p)
         else:
-            dz = g
-        gx = _gemm(dz, weight, ctx.strict, b_mn=True) if ctx.needs_input_grad[0] else None
+            dz = g                                                    # the consumer's dgrad epilogue already applied it
+        gx = None
+        if ctx.needs_input_grad[0]:
+            if ctx.in_mask_scale is not None:                         # x is the producer's ReLU(+Dropout) output
+                gx = _gemm(dz, weight, ctx.strict, b_mn=True, mask_src=x, mask_scale=ctx.in_mask_scale)
+            else:
+                gx = _gemm(dz, weight, ctx.strict, b_mn=True)
         st = ctx.stash
         need_w = ctx.needs_input_grad[1]
         if ctx.role == "small" and st is not None and st.get("has_main", False) and not st.get("main_done", False):
             st.setdefault("pending", []).append((dz, x))
-            return (gx,) + (None,) * 9
+            return (gx,) + (None,) * 11
         gw = gb = None
         if need_w:
             gw = _gemm(dz, x, ctx.strict, a_mn=True, b_mn=True)
@@ -95,13 +117,20 @@ class _LinearFn(Function):
                     if gb is not None:
                         capi.colsum(dzs, out=gb, accumulate=True)
                 st["main_done"] = True
-        return (gx, gw, gb) + (None,) * 7
+        return (gx, gw, gb) + (None,) * 9
 
 
-def linear(x, weight, bias=None, act=ACT_NONE, p=0.0, seed=0, round_out=False, strict=False, stash=None, role=None):
-    """act(x @ weight.T + bias) on the sm_100a fc kernel.  CUDA fp32 only: there is no CPU / library fallback."""
+def linear(x, weight, bias=None, act=ACT_NONE, p=0.0, seed=0, round_out=False, strict=False, stash=None, role=None,
+           in_mask_scale=None, act_bwd_fused=False):
+    """act(x @ weight.T + bias) on the sm_100a fc kernel.  CUDA fp32 only: there is no CPU / library fallback.
+    in_mask_scale (float): `x` is the ReLU(+Dropout) output of a layer created with act_bwd_fused=True whose ONLY
+    consumer is this call -- the input gradient leaves this layer's dgrad epilogue already multiplied by that layer's
+    derivative (in_mask_scale * [x > 0]), and the producer's backward skips its own elementwise pass."""
     if not x.is_cuda:
         raise RuntimeError("the fully-connected block has no CPU implementation (sm_100a kernels only)")
     if x.dim() != 2:
         x = x.reshape(x.shape[0], -1)
-    return _LinearFn.apply(x.float(), weight, bias, int(act), float(p), int(seed), bool(round_out), bool(strict), stash, role)
+    if not FUSE_ACT_BWD and (in_mask_scale is not None or act_bwd_fused):
+        raise RuntimeError("fused activation backward requested while fc.FUSE_ACT_BWD is off")
+    return _LinearFn.apply(x.float(), weight, bias, int(act), float(p), int(seed), bool(round_out), bool(strict), stash, role,
+                           None if in_mask_scale is None else float(in_mask_scale), bool(act_bwd_fused))

@@ -156,6 +156,16 @@ class RoIRegLossComputation(object):
             self._k_event = torch.cuda.Event()
             self._k_event.record()
 
+    @staticmethod
+    def _embed(aug, feature_extractor, model_sim):
+        """Sim_Net(neck(aug)) (loss.py:300-301,304-305).  Sim_Net is the only consumer of this neck call, so fc7's
+        ReLU/Dropout derivative rides in Sim_Net's dgrad epilogue (fc.linear in_mask_scale) when the extractor supports it."""
+        scale = getattr(feature_extractor, "out_act_scale", None)
+        from . import fc
+        if scale is not None and fc.FUSE_ACT_BWD and torch.is_grad_enabled():
+            return model_sim(feature_extractor.forward_neck(aug, fuse_out_bwd=True), in_mask_scale=scale())
+        return model_sim(feature_extractor.forward_neck(aug))
+
     def _augmented_positives_synced(self, st, P, clean_pooled_feats, feature_extractor, model_sim):
         offA_h = st.offA.cpu()                                   # the one host sync of the step
         K = int(offA_h[P]) if P > 0 else 0
@@ -178,7 +188,7 @@ class RoIRegLossComputation(object):
                 drops.append(feature_extractor.drop_pool(Xp))
                 noises.append(feature_extractor.noise_pool(Xp))
             aug = torch.cat(drops + noises, dim=0)
-        E = model_sim(feature_extractor.forward_neck(aug)).contiguous()                  # [2K,128]
+        E = self._embed(aug, feature_extractor, model_sim).contiguous()                  # [2K,128]
         return E, K
 
     def _augmented_positives_speculative(self, st, P, Ncap, clean_pooled_feats, feature_extractor, model_sim):
@@ -195,7 +205,7 @@ class RoIRegLossComputation(object):
         X = _gather(clean_pooled_feats, rows)
         feature_extractor._aug_rows = rows
         aug = torch.cat([feature_extractor.drop_pool(X, seg_off=st.offA), feature_extractor.noise_pool(X)], dim=0)
-        Epad = model_sim(feature_extractor.forward_neck(aug))     # [2Kc,128]
+        Epad = self._embed(aug, feature_extractor, model_sim)     # [2Kc,128]
         j = torch.arange(2 * P * Ncap, device=dev)                # K <= P*Ncap always: every address the kernels form is in range
         jj = j - k64
         pad = j % (2 * Kc)                     # padding entries spread over rows: their (zero) gradients do not pile up on one

@@ -29,14 +29,16 @@ class MISTPredictor(nn.Module):
                 nn.init.normal_(m.weight, mean=0, std=0.001)
                 nn.init.constant_(m.bias, 0)
 
-    def forward(self, x, proposals):
+    def forward(self, x, proposals, in_mask_scale=None):
+        """in_mask_scale: x comes from run_classifier(..., fuse_out_bwd=True) and this is its only consumer."""
         assert x.dim() == 2
         heads = [self.cls_score, self.det_score, self.ref1, self.bbox_pred1, self.ref2, self.bbox_pred2,
                  self.ref3, self.bbox_pred3]
         W = torch.cat([h.weight for h in heads], 0)
         b = torch.cat([h.bias for h in heads], 0)
         from . import fc
-        out = fc.linear(x, W, b, strict=self.strict_fp32).split([h.out_features for h in heads], dim=1)
+        out = fc.linear(x, W, b, strict=self.strict_fp32, in_mask_scale=in_mask_scale) \
+            .split([h.out_features for h in heads], dim=1)
         cls_logit, det_logit, ref1, bb1, ref2, bb2, ref3, bb3 = out
         if not self.training:
             cls_logit = F.softmax(cls_logit, dim=1)

@@ -22,11 +22,14 @@ class Sim_Net(nn.Module):
 
         self.strict_fp32 = False       # True: 3xTF32 split products (parity tests)
 
-    def forward(self, roi_feat):
+    def forward(self, roi_feat, in_mask_scale=None):
+        """in_mask_scale: roi_feat comes from run_classifier(..., fuse_out_bwd=True) and this is its only consumer."""
         from . import fc
+        fuse = fc.FUSE_ACT_BWD and torch.is_grad_enabled()
         h = fc.linear(roi_feat, self.mlp[0].weight, self.mlp[0].bias, act=fc.ACT_RELU, round_out=True,
-                      strict=self.strict_fp32)
-        return F.normalize(fc.linear(h, self.mlp[2].weight, self.mlp[2].bias, strict=self.strict_fp32), dim=1)
+                      strict=self.strict_fp32, in_mask_scale=in_mask_scale, act_bwd_fused=fuse)
+        return F.normalize(fc.linear(h, self.mlp[2].weight, self.mlp[2].bias, strict=self.strict_fp32,
+                                     in_mask_scale=1.0 if fuse else None), dim=1)
 
 
 class _SupConBankFn(Function):

@@ -100,22 +100,30 @@ class VGG16FC67ROIFeatureExtractor(nn.Module):
                     nn.init.normal_(m.weight, 0, 0.01)
                     nn.init.constant_(m.bias, 0)
 
-    def run_classifier(self, x, role=None):
+    def run_classifier(self, x, role=None, fuse_out_bwd=False):
         """self.classifier(x) (vgg16.py:122-130): Linear + ReLU + Dropout twice, each as ONE launch of the tcgen05 fc
         kernel (csrc/fc_gemm.cu) with bias, ReLU, Philox Dropout and TF32 rounding fused into its epilogue.  Same
         parameters, same state-dict keys.  `role` ("main" / "small") marks the two fc6 calls of a training step so their
-        weight gradients leave as one tensor (fc._LinearFn)."""
+        weight gradients leave as one tensor (fc._LinearFn).  fc6's ReLU/Dropout derivative is applied by fc7's dgrad
+        epilogue; with `fuse_out_bwd` the caller promises that every consumer of the result does the same for fc7
+        (fc.linear(..., in_mask_scale=self.out_act_scale())), so no separate elementwise backward pass is left."""
         from . import fc
         c = self.classifier
         stash = self._fc6_stash if (role is not None and self.merge_fc6_wgrad) else None
-        for lin, drop in ((c[1], c[3]), (c[4], c[6])):
-            p = float(drop.p) if self.training else 0.0
-            act = fc.ACT_RELU_DROPOUT if p > 0.0 else fc.ACT_RELU
-            first = lin is c[1]
-            x = fc.linear(x, lin.weight, lin.bias, act=act, p=p, seed=fc.next_dropout_seed() if p > 0.0 else 0,
-                          round_out=True, strict=self.strict_fp32, stash=stash if first else None,
-                          role=role if (first and stash is not None) else None)
+        fuse = fc.FUSE_ACT_BWD and torch.is_grad_enabled()
+        p6 = float(c[3].p) if self.training else 0.0
+        p7 = float(c[6].p) if self.training else 0.0
+        x = fc.linear(x, c[1].weight, c[1].bias, act=fc.ACT_RELU_DROPOUT if p6 > 0.0 else fc.ACT_RELU, p=p6,
+                      seed=fc.next_dropout_seed() if p6 > 0.0 else 0, round_out=True, strict=self.strict_fp32, stash=stash,
+                      role=role if stash is not None else None, act_bwd_fused=fuse)
+        x = fc.linear(x, c[4].weight, c[4].bias, act=fc.ACT_RELU_DROPOUT if p7 > 0.0 else fc.ACT_RELU, p=p7,
+                      seed=fc.next_dropout_seed() if p7 > 0.0 else 0, round_out=True, strict=self.strict_fp32,
+                      in_mask_scale=1.0 / (1.0 - p6) if fuse else None, act_bwd_fused=fuse and fuse_out_bwd)
         return x
+
+    def out_act_scale(self):
+        """1 / (1 - p) of the last Dropout: the scale a consumer passes as in_mask_scale (see run_classifier)."""
+        return 1.0 / (1.0 - (float(self.classifier[6].p) if self.training else 0.0))
 
     def forward(self, x, proposals):                     # vgg16.py:148-153
         self._fc6_stash = None
@@ -128,7 +136,7 @@ class VGG16FC67ROIFeatureExtractor(nn.Module):
         return (self.fuse_clean_aug and self.training and hasattr(self, "dropblock") and self.dropblock.drop_prob > 0
                 and isinstance(self.pooler.poolers[0], ROIPool))
 
-    def forward_clean_and_aug(self, x, proposals):
+    def forward_clean_and_aug(self, x, proposals, fuse_out_bwd=False):
         """weak_head.py:107 + :111-112 in one pass: returns (clean_roi_feats, aug_roi_feats, clean_pooled_feats).
         The same arithmetic as forward() followed by forward_neck(forward_dropblock(pooled)); the two fc6/fc7 passes
         run as one batch, and clean_pooled_feats carries `_odw_gather(rows)` for the contrastive branch (its gradient
@@ -146,7 +154,8 @@ class VGG16FC67ROIFeatureExtractor(nn.Module):
         stash = {}
         buf = pool_and_augment(x[0].float(), rois, (ph, pw), pool.spatial_scale, centres.contiguous(), db.block_size, stash)
         self._fc6_stash = {} if self.merge_fc6_wgrad else None      # one stash per step: main call here, small calls later
-        feats = self.run_classifier(buf.view(2 * R, -1), role="main" if self._fc6_stash is not None else None)
+        feats = self.run_classifier(buf.view(2 * R, -1), role="main" if self._fc6_stash is not None else None,
+                                    fuse_out_bwd=fuse_out_bwd)
         clean, aug = split_rows(feats, R)
         pooled = buf.detach()[:R]
         pooled._odw_gather = lambda rows: gather_rows(buf, rows, R, stash)
@@ -155,8 +164,9 @@ class VGG16FC67ROIFeatureExtractor(nn.Module):
     def forward_pooler(self, x, proposals):
         return self.pooler(x, proposals)
 
-    def forward_neck(self, x):                           # vgg16.py:159-162
-        return self.run_classifier(x.view(x.shape[0], -1), role="small" if self._fc6_stash is not None else None)
+    def forward_neck(self, x, fuse_out_bwd=False):       # vgg16.py:159-162
+        return self.run_classifier(x.view(x.shape[0], -1), role="small" if self._fc6_stash is not None else None,
+                                   fuse_out_bwd=fuse_out_bwd)
 
     def forward_dropblock(self, pooled_feats, proposals):  # vgg16.py:165-167
         return self.dropblock(pooled_feats)

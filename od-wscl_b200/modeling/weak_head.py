@@ -36,9 +36,15 @@ class ROIWeakRegHead(nn.Module):
         fe = self.feature_extractor
         if self.training and self.DB_METHOD == "dropblock" and getattr(fe, "can_fuse_clean_aug", lambda: False)():
             # :107 and :111-112 as ONE fc6/fc7 batch over [clean; DropBlock-augmented] pooled features
-            clean_roi_feats, aug_roi_feats, clean_pooled_feats = fe.forward_clean_and_aug(features, proposals)
-            sim_feature = self.model_sim(clean_roi_feats)                                             # :110
-            cls_score, det_score, ref_scores, ref_bbox_preds = self.predictor(aug_roi_feats, proposals)   # :113
+            # each half of the fc7 output has exactly one consumer, whose dgrad epilogue applies fc7's ReLU/Dropout mask
+            from . import fc
+            fuse = fc.FUSE_ACT_BWD
+            clean_roi_feats, aug_roi_feats, clean_pooled_feats = fe.forward_clean_and_aug(features, proposals,
+                                                                                          fuse_out_bwd=fuse)
+            s7 = fe.out_act_scale() if fuse else None
+            sim_feature = self.model_sim(clean_roi_feats, in_mask_scale=s7)                           # :110
+            cls_score, det_score, ref_scores, ref_bbox_preds = self.predictor(aug_roi_feats, proposals,
+                                                                              in_mask_scale=s7)       # :113
             loss_img, accuracy_img = self.loss_evaluator([cls_score], [det_score], ref_scores, ref_bbox_preds,
                                                          sim_feature, clean_pooled_feats, fe, self.model_sim,
                                                          proposals, targets)                          # :120

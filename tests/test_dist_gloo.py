@@ -21,11 +21,24 @@ def _free_port():
     return p
 
 
+class _CpuHead(torch.nn.Module):
+    """CPU stand-in with MISTPredictor's parameter set and outputs (the product module runs only on the sm_100a fc
+    kernel and refuses CPU tensors); what is under test here is the sharding / all-reduce host logic."""
+
+    def __init__(self, in_channels, nc=21):
+        super().__init__()
+        for n, o in (("cls_score", nc), ("det_score", nc), ("ref1", nc), ("bbox_pred1", 4 * nc), ("ref2", nc),
+                     ("bbox_pred2", 4 * nc), ("ref3", nc), ("bbox_pred3", 4 * nc)):
+            setattr(self, n, torch.nn.Linear(in_channels, o))
+
+    def forward(self, x, proposals):
+        return (self.cls_score(x), self.det_score(x), [self.ref1(x), self.ref2(x), self.ref3(x)],
+                [self.bbox_pred1(x), self.bbox_pred2(x), self.bbox_pred3(x)])
+
+
 def _make_head():
-    from odwscl_b200.config import cfg
-    from odwscl_b200.modeling.predictors import MISTPredictor
     torch.manual_seed(0)
-    m = MISTPredictor(cfg, 64)
+    m = _CpuHead(64)
     for p in m.parameters():                      # the reference init (std 1e-3) makes every gradient tiny
         torch.nn.init.normal_(p, std=0.05)
     return m

@@ -176,3 +176,48 @@ def test_dropblock_segmented_vs_per_call(capi):
     assert float(y[R:].abs().sum()) == 0.0
     gy, _ = capi.dropblock_seg(x.cuda(), cen.cuda(), 1, off, len(seg) - 1, sc)
     assert torch.equal(gy, y)
+
+
+def test_model_gradients_fused_activation_backward(capi):
+    """Folding each ReLU/Dropout derivative into the consumer's dgrad epilogue (fc.FUSE_ACT_BWD) gives the same
+    parameter gradients as the separate elementwise passes, Dropout active, on a full train step."""
+    from oracle import oracle as orc
+    from odwscl_b200.config import cfg
+    from odwscl_b200.modeling import build_detection_model, fc
+    from odwscl_b200.structures import BoxList
+    model = build_detection_model(cfg)
+    model.load_state_dict(orc.synth_state_dict(21, seed=0), strict=True)
+    model.cuda().train()
+    images, boxes, labels = orc.synth_batch(2, 150, 400, 320, 21, seed=31)
+    props = [BoxList(b.cuda(), (400, 320), "xyxy") for b in boxes]
+    targets = []
+    for lab in labels:
+        t = BoxList(torch.zeros((len(lab), 4)), (400, 320), "xyxy")
+        t.add_field("labels", torch.as_tensor(lab))
+        targets.append(t)
+    fe = model.roi_heads.feature_extractor
+
+    def run(fuse):
+        fc.FUSE_ACT_BWD = fuse
+        fc._seed_state["ctr"] = 0                       # same Philox keys in both runs
+        g = torch.Generator().manual_seed(3)
+        sampler = lambda n, h, w, gamma, dev: (torch.rand(n, h, w, generator=g) < gamma).float().to(dev)
+        fe.dropblock.centre_sampler = sampler
+        fe.sim_drop.centre_sampler = sampler
+        gn = torch.Generator().manual_seed(4)
+        fe.noise_sampler = lambda shape, dev: torch.randn(tuple(shape), generator=gn).to(dev)
+        model.zero_grad(set_to_none=True)
+        losses, _ = model(images.cuda(), targets, props)
+        sum(losses.values()).backward()
+        return ({k: float(v) for k, v in losses.items()},
+                {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None})
+    try:
+        l1, g1 = run(True)
+        l0, g0 = run(False)
+    finally:
+        fc.FUSE_ACT_BWD = True
+    assert l1 == l0
+    assert set(g1) == set(g0)
+    for k in g0:
+        torch.testing.assert_close(g1[k], g0[k], rtol=2e-4, atol=2e-4 * float(g0[k].abs().max()) + 1e-12,
+                                   msg=lambda m, k=k: k + ": " + m)
