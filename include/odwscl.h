@@ -208,6 +208,33 @@ int odwscl_fc_gemm_tf32(const float* A, int lda, int a_mn_major, const float* B,
 int odwscl_colsum_f32(const float* x, long long rows, int cols, int ld, float* out, int accumulate,
                       odwscl_stream_t stream);
 
+/* ---- A13 / N2: the MIL + refinement side of RoIRegLossComputation.__call__ (roi_heads/weak_head/loss.py:233-259,
+ * 349-406) over the ONE logits buffer the eight predictor heads leave: logits [R, ld], column blocks
+ * [cls C][det C][ref1 C][bbox1 Q][ref2 C][bbox2 Q][ref3 C][bbox3 Q] (Q = 4*C, or 8 when class-agnostic); C <= 96.
+ * img_off [B+1] int32 = first row of every image.  Replaces ~280 eager torch kernels (forward + autograd backward).
+ *
+ * odwscl_head_scores_f32 (before object discovery): final_score [R,C] = softmax_c(cls) * softmax_over_the_image's_
+ * proposals(det) (loss.py:234-246), sm1 / sm2 [R,C] = softmax_c(ref1 / ref2) (the supervisors of branches 1, 2:
+ * loss.py:283,313), img_score [B,C] = per-image column sums of final_score (loss.py:352); det_max / det_sum [B,C]
+ * (softmax statistics, reused by the loss call) and ref_colsum [3,B,C] (per-image sums of the refinement logits:
+ * the accuracy metric of loss.py:25-34) are scratch outputs. */
+int odwscl_head_scores_f32(const float* logits, int ld, int R, int C, int Q, const int32_t* img_off, int B,
+                           float* det_max, float* det_sum, float* ref_colsum, float* final_score, float* sm1,
+                           float* sm2, float* img_score, odwscl_stream_t stream);
+/* odwscl_head_loss_f32 (after od_layer): pseudo_labels [3,R] int64, label_weights [3,R], reg_targets [3,R,4] as
+ * written by odwscl_od_layer_f32; img_labels [B,C] multi-hot.  out11 = (loss_img, loss_ref_cls0, loss_ref_reg0,
+ * loss_ref_cls1, loss_ref_reg1, loss_ref_cls2, loss_ref_reg2, acc_img, acc_ref0, acc_ref1, acc_ref2), every entry
+ * already divided by B (loss.py:403-406).  grad_logits [R, ld] receives d(sum of the seven losses)/d(logits) in closed
+ * form (every column of the 5C+3Q block is written).  partial: scratch of ceil(R/8)*6 floats. */
+int odwscl_head_loss_f32(const float* logits, int ld, int R, int C, int Q, int cls_agnostic, const int32_t* img_off,
+                         int B, const float* det_max, const float* det_sum, const float* img_score,
+                         const float* img_labels, const int64_t* pseudo_labels, const float* label_weights,
+                         const float* reg_targets, const float* ref_colsum, float eps, float* grad_logits,
+                         float* partial, float* out11, odwscl_stream_t stream);
+/* The backward of that node: column block of loss k scaled in place by upstream7[k] (device; order as out11[0..6]). */
+int odwscl_head_grad_scale_f32(float* grad_logits, int ld, long long R, int C, int Q, const float* upstream7,
+                               odwscl_stream_t stream);
+
 /* ---- A15: DropBlock2D apply (modeling/dropblock/drop_block.py:29-66) with a device-sampled
  * centre mask [R,ph,pw] (1.0 = drop centre): block mask by block x block dilation, global
  * renormalisation numel/sum, y = x * mask * scale in ONE pass over x [R,C,ph,pw].

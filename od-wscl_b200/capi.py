@@ -30,6 +30,7 @@ _LAUNCHES = {
     "odwscl_maxpool2x2_nhwc_bwd_f32": 1, "odwscl_split_tf32": 1,
     "odwscl_relu_dropout_fwd_f32": 1, "odwscl_relu_dropout_bwd_f32": 1, "odwscl_conv_weight_xform_f32": 1,
     "odwscl_fc_gemm_tf32": 1, "odwscl_colsum_f32": 1,
+    "odwscl_head_scores_f32": 3, "odwscl_head_loss_f32": 2, "odwscl_head_grad_scale_f32": 1,
 }
 
 _P, _I, _F, _Z = c_void_p, c_int, c_float, c_size_t
@@ -70,6 +71,9 @@ _SIGS = {
     "odwscl_conv_weight_xform_f32": (_I, [_P, _I, _I, _P, _P, _I, _P]),
     "odwscl_fc_gemm_tf32": (_I, [_P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P, _I, _F, _F, ctypes.c_ulonglong, _I, _P]),
     "odwscl_colsum_f32": (_I, [_P, ctypes.c_longlong, _I, _I, _P, _I, _P]),
+    "odwscl_head_scores_f32": (_I, [_P, _I, _I, _I, _I, _P, _I] + [_P] * 7 + [_P]),
+    "odwscl_head_loss_f32": (_I, [_P, _I, _I, _I, _I, _I, _P, _I] + [_P] * 8 + [_F, _P, _P, _P, _P]),
+    "odwscl_head_grad_scale_f32": (_I, [_P, _I, ctypes.c_longlong, _I, _I, _P, _P]),
     "odwscl_version": (_I, []),
     "odwscl_strerror": (ctypes.c_char_p, [_I]),
 }
@@ -566,6 +570,54 @@ def colsum(x, out=None, accumulate=False):
     with torch.cuda.device(x.device):
         _call("odwscl_colsum_f32", _ptr(x), rows, cols, int(ld), _ptr(out), int(accumulate), _stream())
     return out
+
+
+# ---------------------------------------------------------------- MIL + refinement losses (csrc/head_loss.cu)
+class HeadScores:
+    """Outputs of head_scores: what object discovery reads (final_score, sm1, sm2) + the statistics the loss reuses."""
+    pass
+
+
+def head_scores(logits, C, Q, img_off, B):
+    """logits [R, >= 5C+3Q] (row pitch = stride(0)), img_off int32 [B+1] on the device."""
+    logits, ld = _rows2d(logits, "logits")
+    R = logits.shape[0]
+    dev = logits.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    hs = HeadScores()
+    hs.logits, hs.ld, hs.R, hs.C, hs.Q, hs.B, hs.img_off = logits, ld, R, C, Q, B, img_off
+    hs.det_max, hs.det_sum = torch.empty((B, C), **f32), torch.empty((B, C), **f32)
+    hs.ref_colsum = torch.empty((3, B, C), **f32)
+    hs.final_score, hs.sm1, hs.sm2 = (torch.empty((R, C), **f32) for _ in range(3))
+    hs.img_score = torch.empty((B, C), **f32)
+    with torch.cuda.device(dev):
+        _call("odwscl_head_scores_f32", _ptr(logits), int(ld), R, C, Q, _ptr(_chk(img_off, torch.int32, "img_off")), B,
+              _ptr(hs.det_max), _ptr(hs.det_sum), _ptr(hs.ref_colsum), _ptr(hs.final_score), _ptr(hs.sm1), _ptr(hs.sm2),
+              _ptr(hs.img_score), _stream())
+    return hs
+
+
+def head_loss(hs, img_labels, pl, lw, rt, cls_agnostic, eps):
+    """-> (out11 [11] = 7 losses + 4 accuracies (already / B), grad_logits [R, ld])."""
+    dev = hs.logits.device
+    out = torch.empty((11,), dtype=torch.float32, device=dev)
+    grad = torch.empty((hs.R, hs.ld), dtype=torch.float32, device=dev)
+    if hs.ld > 5 * hs.C + 3 * hs.Q:
+        grad[:, 5 * hs.C + 3 * hs.Q:].zero_()                   # pitch padding columns
+    partial = torch.empty((max((hs.R + 7) // 8, 1) * 6,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _call("odwscl_head_loss_f32", _ptr(hs.logits), int(hs.ld), hs.R, hs.C, hs.Q, int(cls_agnostic), _ptr(hs.img_off),
+              hs.B, _ptr(hs.det_max), _ptr(hs.det_sum), _ptr(hs.img_score), _ptr(_chk(img_labels, torch.float32, "labels")),
+              _ptr(_chk(pl, torch.int64, "pl")), _ptr(_chk(lw, torch.float32, "lw")), _ptr(_chk(rt, torch.float32, "rt")),
+              _ptr(hs.ref_colsum), float(eps), _ptr(grad), _ptr(partial), _ptr(out), _stream())
+    return out, grad
+
+
+def head_grad_scale_(grad, C, Q, upstream7):
+    with torch.cuda.device(grad.device):
+        _call("odwscl_head_grad_scale_f32", _ptr(grad), int(grad.stride(0)), grad.shape[0], C, Q,
+              _ptr(_chk(upstream7, torch.float32, "upstream")), _stream())
+    return grad
 
 
 # ---------------------------------------------------------------- object discovery / SupCon

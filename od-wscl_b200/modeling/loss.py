@@ -18,7 +18,6 @@ import torch.nn.functional as F
 
 from .. import capi
 from ..config import cfg as global_cfg
-from ..layers import smooth_l1_loss
 from . import registry
 from .sim_head import SupConLossV2, supcon_bank_loss
 
@@ -34,6 +33,35 @@ def _host_labels(target):
     if isinstance(lab, torch.Tensor):
         lab = lab.cpu()
     return sorted(set(int(x) for x in lab))
+
+
+class _HeadLossFn(torch.autograd.Function):
+    """(loss_img, loss_ref_cls0, loss_ref_reg0, ..., loss_ref_reg2, acc_img, acc_ref0..2) of loss.py:349-406 from the
+    heads' logits buffer (csrc/head_loss.cu).  The forward already writes d(sum of losses)/d(logits) in closed form; the
+    backward only scales the column block of every loss by its upstream gradient."""
+
+    @staticmethod
+    def forward(ctx, logits, hs, img_labels, pl, lw, rt, cls_agnostic, eps):
+        out, grad = capi.head_loss(hs, img_labels, pl, lw, rt, cls_agnostic, eps)
+        ctx.save_for_backward(grad)
+        ctx.C, ctx.Q, ctx.width = hs.C, hs.Q, logits.shape[1]
+        res = out.unbind(0)                 # 11 scalars: no select / scatter nodes in the autograd graph
+        ctx.mark_non_differentiable(*res[7:])
+        return res
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, *gs):
+        (grad,) = ctx.saved_tensors
+        zero = None
+        up = []
+        for g in gs[:7]:
+            if g is None:
+                zero = grad.new_zeros(()) if zero is None else zero
+                g = zero
+            up.append(g.reshape(()).float())
+        capi.head_grad_scale_(grad, ctx.C, ctx.Q, torch.stack(up))
+        return (grad[:, :ctx.width],) + (None,) * 7
 
 
 @registry.ROI_WEAK_LOSS.register("RoIRegLoss")
@@ -73,21 +101,15 @@ class RoIRegLossComputation(object):
                  feature_extractor, model_sim, proposals, targets, epsilon=1e-8):
         sizes = [len(p) for p in proposals]
         B, R = len(sizes), sum(sizes)
-        class_score = F.softmax(torch.cat(class_score, dim=0), dim=1)                     # loss.py:234
-        det_score = torch.cat(det_score, dim=0)
-        C = class_score.shape[1]
-        dev = class_score.device
-        same = all(s == sizes[0] for s in sizes)
-        if same:
-            # loss.py:237-244: softmax over the proposals of each image.  Done along a contiguous last axis
-            # ([B,C,N]): torch's strided-dim softmax kernel takes 60 + 77 us (fwd + bwd) on this 84 k-element tensor
-            final_det = F.softmax(det_score.view(B, sizes[0], C).transpose(1, 2).contiguous(), dim=2) \
-                .transpose(1, 2).reshape(R, C)
-        else:
-            final_det = torch.cat([F.softmax(d, dim=0) for d in det_score.split(sizes)], dim=0)
-        final_score = class_score * final_det                                             # loss.py:246
-        ref_sm = [F.softmax(r, dim=1) for r in ref_scores]
-
+        # the eight heads' logits as ONE [R, 5C+3Q] buffer (what MISTPredictor's single GEMM leaves); pieces handed in
+        # separately (tests, foreign predictors) are concatenated once
+        C = class_score[0].shape[1]
+        Q = ref_bbox_preds[0].shape[1]
+        logits = getattr(class_score[0], "_odw_logits", None) if len(class_score) == 1 else None
+        if logits is None or logits.shape[1] != 5 * C + 3 * Q:
+            logits = torch.cat([torch.cat(class_score, dim=0), torch.cat(det_score, dim=0), ref_scores[0],
+                                ref_bbox_preds[0], ref_scores[1], ref_bbox_preds[1], ref_scores[2], ref_bbox_preds[2]], dim=1)
+        dev = logits.device
         # ---- host-side bookkeeping from the (host) image labels: pairs, offsets, multi-hot labels
         pos = [[c - 1 for c in _host_labels(t) if c > 0] for t in targets]               # loss.py:270
         pair_img = [b for b in range(B) for _ in pos[b]]
@@ -105,16 +127,11 @@ class RoIRegLossComputation(object):
         img_labels_d = img_labels.pin_memory().to(dev, non_blocking=True)
         boxes = torch.cat([p.bbox for p in proposals], dim=0).float().contiguous()
         Ncap = max(sizes)
-
-        losses = dict(loss_img=0)
-        accs = dict(acc_img=0)
-        for i in range(3):
-            losses["loss_ref_cls%d" % i] = 0
-            losses["loss_ref_reg%d" % i] = 0
-            accs["acc_ref%d" % i] = 0
+        # ---- loss.py:234-259: class softmax x per-image proposal softmax, supervisors of the refinement branches
+        hs = capi.head_scores(logits.detach(), C, Q, img_off_d, B)
 
         # ---- contrastive object discovery (loss.py:271-347)
-        scores = (final_score.detach().contiguous(), ref_sm[0].detach().contiguous(), ref_sm[1].detach().contiguous())
+        scores = (hs.final_score, hs.sm1, hs.sm2)
         Fm = sim_feature.contiguous()
         st = capi.discover_phase_a(boxes, img_off_d, scores, pair_img_d, pair_cls_d, Ncap, self.p_thres)
         spec = self.speculative_k and self.batch_aug and P > 0 and self._poll_k_cap() is not None
@@ -127,10 +144,18 @@ class RoIRegLossComputation(object):
         capi.bank_assemble(st, C - 1, Mcap)
         st.E = E.detach()                       # [2K,128] augmented-positive embeddings (drop rows, then noise rows)
         self.last_state = st
-        losses["loss_sim"] = self.sim_lmda * supcon_bank_loss(Fm, E, st.row_src, st.row_lab, st.row_w, st.M, Mcap,
-                                                              self.temp)               # loss.py:347
-        return self._refinement_losses(st, losses, accs, final_score, ref_scores, ref_bbox_preds, img_labels_d, sizes,
-                                       offs, pos, same, B, R, C, dev, epsilon)
+        loss_sim = self.sim_lmda * supcon_bank_loss(Fm, E, st.row_src, st.row_lab, st.row_w, st.M, Mcap,
+                                                    self.temp)                         # loss.py:347
+        # ---- pseudo labels (loss.py:364-368 -> od_layer) and the MIL + refinement losses (loss.py:349-406)
+        pl, lw, rt = capi.od_layer(st, self.fg_thresh)
+        out = _HeadLossFn.apply(logits, hs, img_labels_d, pl, lw, rt, bool(self.cls_agnostic_bbox_reg), float(epsilon))
+        losses = {"loss_img": out[0]}
+        for i in range(3):
+            losses["loss_ref_cls%d" % i] = out[1 + 2 * i]
+            losses["loss_ref_reg%d" % i] = out[2 + 2 * i]
+        losses["loss_sim"] = loss_sim
+        accs = {"acc_img": out[7], "acc_ref0": out[8], "acc_ref1": out[9], "acc_ref2": out[10]}
+        return losses, accs
 
     # ------------------------------------------------------------------ augmented positives (loss.py:299-310)
     def _poll_k_cap(self):
@@ -215,63 +240,6 @@ class RoIRegLossComputation(object):
         self.overflow = (k64 > Kc).float()
         self._record_k(kdev)
         return E, Kc
-
-    def _refinement_losses(self, st, losses, accs, final_score, ref_scores, ref_bbox_preds, img_labels_d, sizes, offs,
-                           pos, same, B, R, C, dev, epsilon):
-        # ---- pseudo labels for the three refinement branches (loss.py:364-368 -> od_layer)
-        pl, lw, rt = capi.od_layer(st, self.fg_thresh)
-
-        # ---- MIL + refinement losses (loss.py:349-400), vectorised over images
-        inv_n = torch.tensor([1.0 / s for s in sizes for _ in range(s)], dtype=torch.float32).pin_memory() \
-            .to(dev, non_blocking=True) if not same else None
-
-        def per_image_mean_sum(v):          # sum_b mean_{j in image b} v_j
-            if same:
-                return v.sum() / sizes[0]
-            return (v * inv_n).sum()
-
-        if same:
-            img_score = final_score.view(B, sizes[0], C).sum(1)
-        else:
-            img_score = torch.stack([f.sum(0) for f in final_score.split(sizes)])
-        img_score = torch.clamp(img_score, min=epsilon, max=1 - epsilon)                 # loss.py:353
-        losses["loss_img"] = F.binary_cross_entropy(img_score, img_labels_d, reduction="none").mean(1).sum()
-        ar4 = torch.arange(4, device=dev)
-        for i in range(3):
-            lmda = 3 if i == 0 else 1                                                    # loss.py:373
-            ce = F.cross_entropy(ref_scores[i], pl[i], reduction="none") * lw[i]
-            losses["loss_ref_cls%d" % i] = lmda * per_image_mean_sum(ce)
-            fg = (pl[i] > 0).float()
-            map_inds = (ar4[None] + 4).expand(R, 4) if self.cls_agnostic_bbox_reg else 4 * pl[i][:, None] + ar4[None]
-            sl1 = smooth_l1_loss(ref_bbox_preds[i].gather(1, map_inds), rt[i], beta=1, reduction=False)
-            losses["loss_ref_reg%d" % i] = lmda * per_image_mean_sum((sl1 * (lw[i] * fg)[:, None]).sum(1))
-
-        with torch.no_grad():               # compute_avg_img_accuracy (loss.py:25-34) without .item(), batched over
-            # images: top-kmax once, positions past each image's own k masked out (same indices as per-image topk(k))
-            ks = [max(len(pos[b]), 1) for b in range(B)]
-            kmax = max(ks)
-            k_d = torch.tensor(ks, dtype=torch.float32).pin_memory().to(dev, non_blocking=True)
-            keep = (torch.arange(kmax, device=dev)[None] < k_d[:, None]).float()          # [B,kmax]
-
-            def topk_label_mean(score, labels):            # sum_b mean(labels[b][topk_k_b(score[b])])
-                idx = score.topk(kmax, dim=1)[1]
-                return ((labels.gather(1, idx) * keep).sum(1) / k_d).sum()
-
-            accs["acc_img"] = accs["acc_img"] + topk_label_mean(img_score, img_labels_d)
-            for i in range(3):
-                if same:
-                    rs = ref_scores[i].view(B, sizes[0], C).sum(1)
-                else:
-                    rs = torch.stack([r.sum(0) for r in ref_scores[i].split(sizes)])
-                accs["acc_ref%d" % i] = accs["acc_ref%d" % i] + topk_label_mean(rs[:, 1:], img_labels_d[:, 1:])
-
-        for k in losses:
-            if "sim" in k:
-                continue
-            losses[k] = losses[k] / B                                                     # loss.py:403-406
-        for k in accs:
-            accs[k] = accs[k] / B
-        return losses, accs
 
 
 def make_roi_weak_loss_evaluator(cfg):

@@ -37,9 +37,10 @@ class MISTPredictor(nn.Module):
         W = torch.cat([h.weight for h in heads], 0)
         b = torch.cat([h.bias for h in heads], 0)
         from . import fc
-        out = fc.linear(x, W, b, strict=self.strict_fp32, in_mask_scale=in_mask_scale) \
-            .split([h.out_features for h in heads], dim=1)
-        cls_logit, det_logit, ref1, bb1, ref2, bb2, ref3, bb3 = out
+        y = fc.linear(x, W, b, strict=self.strict_fp32, in_mask_scale=in_mask_scale)
+        cls_logit, det_logit, ref1, bb1, ref2, bb2, ref3, bb3 = y.split([h.out_features for h in heads], dim=1)
+        if self.training:
+            cls_logit._odw_logits = y      # the loss consumes the eight heads as one buffer (csrc/head_loss.cu)
         if not self.training:
             cls_logit = F.softmax(cls_logit, dim=1)
             det_logit = torch.cat([F.softmax(d, dim=0) for d in det_logit.split([len(p) for p in proposals])], 0)

@@ -350,3 +350,78 @@ def test_full_step_other_configs(name, B, N, W, H, C):
         if clean_spec_passes >= 1:
             break
     assert clean_spec_passes >= 1, "no speculative pass completed without overflow"
+
+
+@pytest.mark.parametrize("sizes,C,agn", [([300, 211], 21, False), ([500], 81, False), ([64, 64, 64], 21, True)])
+def test_head_loss_kernels_vs_torch(sizes, C, agn):
+    """csrc/head_loss.cu (scores, seven losses, four accuracies, closed-form logits gradient) against an fp64 torch
+    restatement of loss.py:234-259,349-406 with autograd."""
+    from odwscl_b200 import capi
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(sum(sizes) + C)
+    B, R = len(sizes), sum(sizes)
+    Q = 8 if agn else 4 * C
+    W = 5 * C + 3 * Q
+    logits = (torch.randn(R, W, generator=g) * 1.5).cuda()
+    off = [0]
+    for n in sizes:
+        off.append(off[-1] + n)
+    img_off = torch.tensor(off, dtype=torch.int32).cuda()
+    labels = torch.zeros(B, C)
+    for b in range(B):
+        labels[b, torch.randperm(C - 1, generator=g)[: 1 + b % 3] + 1] = 1.0
+    pl = torch.randint(0, C, (3, R), generator=g)
+    pl[:, ::3] = 0                                     # a share of background rows
+    lw = torch.rand(3, R, generator=g)
+    rt = torch.randn(3, R, 4, generator=g) * 1.5       # both smooth-L1 regimes
+    hs = capi.head_scores(logits, C, Q, img_off, B)
+    out, grad = capi.head_loss(hs, labels.cuda(), pl.cuda(), lw.cuda(), rt.cuda(), agn, 1e-8)
+    # ---- fp64 restatement
+    z = logits.double().cpu().requires_grad_(True)
+    cls, det = z[:, :C], z[:, C:2 * C]
+    refs = [z[:, 2 * C + i * (C + Q): 3 * C + i * (C + Q)] for i in range(3)]
+    bbs = [z[:, 3 * C + i * (C + Q): 3 * C + i * (C + Q) + Q] for i in range(3)]
+    final = F.softmax(cls, 1) * torch.cat([F.softmax(d, 0) for d in det.split(sizes)])
+    torch.testing.assert_close(hs.final_score.cpu().double(), final.detach(), rtol=2e-5, atol=1e-9)
+    torch.testing.assert_close(hs.sm1.cpu().double(), F.softmax(refs[0], 1).detach(), rtol=2e-5, atol=1e-9)
+    torch.testing.assert_close(hs.sm2.cpu().double(), F.softmax(refs[1], 1).detach(), rtol=2e-5, atol=1e-9)
+    L = [0.0] * 7
+    acc = [0.0] * 4
+    ar4 = torch.arange(4)
+
+    def topk_acc(score, lab):
+        k = max(int(lab.sum()), 1)
+        return float(lab[score.topk(k)[1]].mean()) if lab.numel() else 0.0
+    labd = labels.double()
+    for b, (f, n) in enumerate(zip(final.split(sizes), sizes)):
+        img = torch.clamp(f.sum(0), 1e-8, 1 - 1e-8)
+        L[0] = L[0] + F.binary_cross_entropy(img, labd[b])
+        kk = max(int(labels[b].sum()), 1)
+        acc[0] += float(labd[b][img.topk(kk)[1]].sum() / kk)
+        for i in range(3):
+            lm = 3 if i == 0 else 1
+            zi = refs[i][off[b]:off[b + 1]]
+            pli, lwi = pl[i, off[b]:off[b + 1]], lw[i, off[b]:off[b + 1]].double()
+            L[1 + 2 * i] = L[1 + 2 * i] + lm * (F.cross_entropy(zi, pli, reduction="none") * lwi).mean()
+            fg = (pli > 0).double()
+            idx = (ar4[None] + 4).expand(n, 4) if agn else 4 * pli[:, None] + ar4[None]
+            d = (bbs[i][off[b]:off[b + 1]].gather(1, idx) - rt[i, off[b]:off[b + 1]].double()).abs()
+            sl = torch.where(d < 1, 0.5 * d * d, d - 0.5)
+            L[2 + 2 * i] = L[2 + 2 * i] + lm * ((sl * (lwi * fg)[:, None]).sum(1)).mean()
+            rs = zi.sum(0)[1:]
+            acc[1 + i] += float(labd[b][1:][rs.topk(kk)[1]].sum() / kk)
+    total = sum(L) / B
+    total.backward()
+    got = out.cpu().double()
+    for k in range(7):
+        assert abs(float(got[k]) - float(L[k]) / B) <= 2e-5 * abs(float(L[k]) / B) + 1e-9, (k, float(got[k]), float(L[k]) / B)
+    for k in range(4):
+        assert abs(float(got[7 + k]) - acc[k] / B) <= 1e-6, (k, float(got[7 + k]), acc[k] / B)
+    torch.testing.assert_close(grad[:, :W].cpu().double(), z.grad, rtol=1e-4, atol=1e-7 * float(z.grad.abs().max()) + 1e-12)
+    # upstream scaling: block k scaled by g[k]
+    up = torch.tensor([2.0, 0.5, 3.0, 1.0, 0.0, -1.0, 4.0]).cuda()
+    g2 = capi.head_grad_scale_(grad.clone(), C, Q, up)
+    blk = lambda k: (slice(0, 2 * C) if k == 0 else
+                     (lambda i, r: slice(2 * C + i * (C + Q) + (C if r else 0), 2 * C + i * (C + Q) + (C + Q if r else C)))((k - 1) // 2, (k - 1) % 2))
+    for k in range(7):
+        torch.testing.assert_close(g2[:, blk(k)], grad[:, blk(k)] * up[k], rtol=1e-6, atol=0)
