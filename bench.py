@@ -29,6 +29,37 @@ IMG_W, IMG_H, N_PROP, B_PER_GPU, NUM_CLASSES = 1000, 600, 2000, 2, 21
 METRIC = "proposals/sec (2000 ROIs/img, 1000x600)"
 WORKLOAD = ("BASELINE configs[1]: bs=2/GPU, 2000 MCG-style proposals/img, 1000x600 (pad 608x1024), VGG16-OICR, 21 classes, "
             "fwd+bwd+SGD")
+# BASELINE.json `configs`: [1] is the configuration the metric is quoted on (the default, weak scaling: 2 images per GPU);
+# [2]..[4] fix the GLOBAL batch at 8 images (strong scaling: 8 / world images per GPU).  `scales` = short sides of the
+# multi-scale config on 500x375-aspect images; every step of a rank uses one scale, cycling through the list.
+CONFIGS = {
+    1: dict(name="BASELINE configs[1]", W=1000, H=600, N=2000, C=21, per_gpu=2, global_batch=None, scales=None,
+            what="bs=2/GPU, 2000 MCG-style proposals/img, 1000x600 (pad 608x1024)"),
+    2: dict(name="BASELINE configs[2]", W=1000, H=600, N=2000, C=21, per_gpu=None, global_batch=8, scales=None,
+            what="global bs=8, 2000 proposals/img, 1000x600, nms 0.1 temp 0.2, full train step"),
+    3: dict(name="BASELINE configs[3]", W=1600, H=1200, N=2000, C=21, per_gpu=None, global_batch=8,
+            scales=[(640, 480), (768, 576), (917, 688), (1152, 864), (1600, 1200)],
+            what="global bs=8, VOC12-shape multi-scale {480,576,688,864,1200}, 2000 proposals/img, one scale per step"),
+    4: dict(name="BASELINE configs[4]", W=1000, H=600, N=4000, C=81, per_gpu=None, global_batch=8, scales=None,
+            what="global bs=8, COCO-shape: 4000 MCG proposals/img, 81 classes"),
+}
+
+
+def apply_config(idx, world):
+    """Set the module-level workload constants from BASELINE config `idx`; returns the scaling mode."""
+    global IMG_W, IMG_H, N_PROP, B_PER_GPU, NUM_CLASSES, WORKLOAD, METRIC
+    c = CONFIGS[idx]
+    IMG_W, IMG_H, N_PROP, NUM_CLASSES = c["W"], c["H"], c["N"], c["C"]
+    if c["global_batch"] is not None:
+        if c["global_batch"] % world:
+            raise SystemExit("config %d: global batch %d is not divisible by %d GPUs" % (idx, c["global_batch"], world))
+        B_PER_GPU = c["global_batch"] // world
+    else:
+        B_PER_GPU = c["per_gpu"]
+    WORKLOAD = "%s: %s, VGG16-OICR, %d classes, fwd+bwd+SGD" % (c["name"], c["what"], NUM_CLASSES)
+    if idx != 1:
+        METRIC = "proposals/sec (%d ROIs/img, %s)" % (N_PROP, "multi-scale" if c["scales"] else "%dx%d" % (IMG_W, IMG_H))
+    return "weak" if c["global_batch"] is None else "strong"
 
 
 def parse():
@@ -36,7 +67,8 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "stock-gpu"])
+    ap.add_argument("--config", type=int, default=1, choices=sorted(CONFIGS), help="BASELINE.json configs[i] (default 1)")
     ap.add_argument("--strict-fp32", action="store_true", help="disable TF32 tensor-core math in torch GEMM/conv")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--k-margin", type=float, default=1.5, help="bound on K = margin * largest K seen + 64, on a --k-granule grid")
@@ -94,39 +126,53 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------ CPU arm
-def cpu_oracle_rate(n_props, steps=1, warmup=0):
-    """Reference arm / cpu_baseline: the oracle port (oracle/oracle.py::model_forward, torch-CPU +
-    C ROIPool) of the same path, forward + backward, on the host cores.  Bounded sample: ONE
-    1000x600 image with `n_props` proposals per step."""
+def cpu_oracle_rate(n_props, steps=1, warmup=0, n_images=1, optimizer=False):
+    """Reference arm / cpu_baseline: the oracle port (oracle/oracle.py::model_forward, torch-CPU + C ROIPool) of the same
+    path on the host cores, all threads: forward + backward (+ the SGD update of solver/build.py:10-24 when
+    `optimizer`).  One step = `n_images` synthetic images of the configured size with `n_props` proposals each."""
     import torch
     from oracle import oracle as orc
     torch.set_num_threads(os.cpu_count() or 1)
     sd = {k: v.clone().requires_grad_(not k.split(".")[3] in ("0", "2", "5", "7") if k.startswith("backbone") else True)
           for k, v in orc.synth_state_dict(NUM_CLASSES, seed=0).items()}
-    images, boxes, labels = orc.synth_batch(1, n_props, IMG_W, IMG_H, NUM_CLASSES, seed=1234)
+    opt = None
+    if optimizer:
+        wts = [v for k, v in sd.items() if v.requires_grad and "bias" not in k]
+        bia = [v for k, v in sd.items() if v.requires_grad and "bias" in k]
+        opt = torch.optim.SGD([{"params": wts, "lr": 0.01, "weight_decay": 0.0001},
+                               {"params": bia, "lr": 0.02, "weight_decay": 0.0}], lr=0.01, momentum=0.9)
+    images, boxes, labels = orc.synth_batch(n_images, n_props, IMG_W, IMG_H, NUM_CLASSES, seed=1234)
     times = []
     for it in range(warmup + steps):
+        t0 = time.perf_counter()
         for v in sd.values():
             v.grad = None
-        t0 = time.perf_counter()
         losses = orc.model_forward(sd, images, boxes, labels, orc.StochasticSource(7 + it, dropout=True))
         sum(losses.values()).backward()
+        if opt is not None:
+            opt.step()
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
     sec = sum(times) / len(times)
-    return n_props / sec, sec, torch.get_num_threads()
+    return n_images * n_props / sec, sec, torch.get_num_threads()
 
 
 def run_reference(args):
+    """`--impl reference`: the CPU arm on OUR arm's config -- same image size, proposals per image, classes, images
+    per step (capped at 2 so that --steps K --warmup W ends within minutes: the sample is stated), forward + backward +
+    SGD, exactly K timed steps after W warm-up steps."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    rate, sec, cores = cpu_oracle_rate(args.cpu_sample_props, steps=max(1, min(args.steps, 3)), warmup=min(args.warmup, 1))
-    sample = "oracle port (oracle/oracle.py, torch-CPU + C ROIPool): 1 image 1000x600, %d proposals, fwd+bwd per step" % args.cpu_sample_props
+    n_img = min(B_PER_GPU, 2)
+    rate, sec, cores = cpu_oracle_rate(N_PROP, steps=max(1, args.steps), warmup=max(0, args.warmup), n_images=n_img,
+                                       optimizer=True)
+    sample = ("oracle port (oracle/oracle.py, torch-CPU + C ROIPool): %d image(s) %dx%d x %d proposals per step, "
+              "fwd+bwd+SGD, %d threads" % (n_img, IMG_W, IMG_H, N_PROP, cores))
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "proposals/s", "n_gpus": args.gpus,
-            "steps": max(1, min(args.steps, 3)), "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "steps": max(1, args.steps), "warmup": max(0, args.warmup), "ms_per_step": sec * 1e3,
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "images_per_gpu": B_PER_GPU, "proposals_per_image": N_PROP,
                        "sample": "bounded CPU sample per step: " + sample},
             "cpu_baseline": {"value": rate, "unit": "proposals/s", "cores": cores, "kind": "port", "sample": sample},
@@ -169,25 +215,35 @@ def run_ours(args):
     torch.backends.cudnn.benchmark = True
     capi.lib()
 
-    torch.manual_seed(0)
-    model = build_detection_model(cfg).to(dev).train()
+    from odwscl_b200.config import get_cfg_defaults
+    mcfg = get_cfg_defaults()
+    mcfg.MODEL.ROI_BOX_HEAD.NUM_CLASSES = NUM_CLASSES
+    torch.manual_seed(0)              # identical initial weights on every rank
+    model = build_detection_model(mcfg).to(dev).train()
+    torch.manual_seed(1000 + rank)    # per-rank DropBlock / noise / Dropout streams (the reference leaves ranks independent)
     opt = make_optimizer(model)
     step_model = model
     if world > 1:
         step_model = sharding.wrap_ddp(model, dev)
-    images_h, rois_h, boxes, labels = synth_batch(B_PER_GPU, N_PROP, IMG_W, IMG_H, NUM_CLASSES,
-                                                  seed=sharding.rank_seed(1234, rank, B_PER_GPU), pin=True)
-    targets = []
-    for lab in labels:
-        t = BoxList(torch.zeros((len(lab), 4)), (IMG_W, IMG_H), "xyxy")
-        t.add_field("labels", torch.as_tensor(lab))       # host labels: no device round trip in the loss
-        targets.append(t)
-    sizes = [b.shape[0] for b in boxes]
+    # one host batch per scale (a single one unless the config is multi-scale); a rank's step i uses batch (i + rank) % n,
+    # so with multi-scale the ranks see different shapes in the same step, as the reference's per-image random scale does
+    scales = CONFIGS[args.config]["scales"] or [(IMG_W, IMG_H)]
+    batches = []
+    for si, (bw, bh) in enumerate(scales):
+        im_h, ro_h, boxes, labels = synth_batch(B_PER_GPU, N_PROP, bw, bh, NUM_CLASSES,
+                                                seed=sharding.rank_seed(1234 + 1000 * si, rank, B_PER_GPU), pin=True)
+        tg = []
+        for lab in labels:
+            t = BoxList(torch.zeros((len(lab), 4)), (bw, bh), "xyxy")
+            t.add_field("labels", torch.as_tensor(lab))       # host labels: no device round trip in the loss
+            tg.append(t)
+        batches.append(dict(images_h=im_h, rois_h=ro_h, sizes=[b.shape[0] for b in boxes], targets=tg, wh=(bw, bh)))
     loss_h = torch.zeros((2,), dtype=torch.float32).pin_memory()          # (loss, overflow flag)
     redone = [0]
+    counter = {"resident": rank, "e2e": rank, "fed": rank}
 
-    def props_from(rois_d):
-        return [BoxList(r[:, 1:], (IMG_W, IMG_H), "xyxy") for r in rois_d.split(sizes)]
+    def props_from(rois_d, bt):
+        return [BoxList(r[:, 1:], bt["wh"], "xyxy") for r in rois_d.split(bt["sizes"])]
 
     # No host synchronisation inside the step: the contrastive branch sizes its augmented batch from a bound on K
     # (speculative_k) and raises `overflow` on the device when the bound was too small; the fused optimizer takes it
@@ -197,7 +253,7 @@ def run_ours(args):
     evaluator.k_margin, evaluator.k_granule = args.k_margin, args.k_granule
     overflow_log = []
 
-    def step(images_d, props):
+    def step(images_d, props, targets):
         losses, _ = step_model(images_d, targets, props)
         total = sum(losses.values())
         opt.zero_grad(set_to_none=True)
@@ -240,22 +296,32 @@ def run_ours(args):
             print("[bench] %s host enqueue ms: %s  K bound: %s" % (tag, host_ms, caps), file=sys.stderr, flush=True)
         return sharding.max_over_ranks(evs[0].elapsed_time(evs[n]), dev)
 
-    images_d = images_h.to(dev, non_blocking=True)
-    rois_d = rois_h.to(dev, non_blocking=True)
-    props_d = props_from(rois_d)
+    for bt in batches:
+        bt["images_d"] = bt["images_h"].to(dev, non_blocking=True)
+        bt["rois_d"] = bt["rois_h"].to(dev, non_blocking=True)
+        bt["props_d"] = props_from(bt["rois_d"], bt)
 
     def resident_step():
-        step(images_d, props_d)
+        bt = batches[counter["resident"] % len(batches)]
+        counter["resident"] += 1
+        step(bt["images_d"], bt["props_d"], bt["targets"])
 
     from odwscl_b200.data import HostPrefetcher
     prefetch = HostPrefetcher(dev)
-    prefetch.feed(images_h, rois_h)
+
+    def feed_next():
+        bt = batches[counter["fed"] % len(batches)]
+        counter["fed"] += 1
+        prefetch.feed(bt["images_h"], bt["rois_h"])
+        return bt
+    in_flight = [feed_next()]
 
     def e2e_step():
         for attempt in range(3):
+            bt = in_flight.pop(0)
             im, ro = prefetch.next()                       # this step's inputs: H2D issued during the previous step
-            prefetch.feed(images_h, rois_h)                # next step's H2D (pinned host -> device) on the copy stream
-            total = step(im, props_from(ro))
+            in_flight.append(feed_next())                  # next step's H2D (pinned host -> device) on the copy stream
+            total = step(im, props_from(ro, bt), bt["targets"])
             flag = evaluator.overflow if evaluator.overflow is not None else total.new_zeros(1)
             loss_h.copy_(torch.cat([total.detach().view(1), flag.view(1)]), non_blocking=True)
             torch.cuda.current_stream().synchronize()      # the user reads the loss every step
@@ -267,9 +333,14 @@ def run_ours(args):
     # land inside the timed region; only the samples taken inside the timed regions are kept.
     sampler = ClockSampler(local)
     sampler.start()
-    # untimed warm-up: at least 8 steps -- the first steps size the speculative batch bound, fill the caching allocator
-    # and cuBLAS's heuristics cache for the padded shapes (step_trace.py: steps 2-4 take 40-65 ms, then 18-19 ms)
-    n_warm = max(args.warmup, 8)
+    # calibration (part of the set-up, like cudnn.benchmark autotuning): the first steps size the speculative batch bound
+    # and the split-K workspaces and fill the caching allocator (steps 2-4 take 40-65 ms, then ~15 ms); every shape of a
+    # multi-scale config is visited.  Then exactly --warmup untimed steps, then the timed ones.
+    n_calib = max(5, 2 * len(batches))
+    for _ in range(n_calib):
+        resident_step()
+    torch.cuda.synchronize()
+    n_warm = args.warmup
     for _ in range(n_warm):
         resident_step()
     torch.cuda.synchronize()
@@ -290,9 +361,11 @@ def run_ours(args):
         torch.cuda.profiler.stop()
     launches = capi.launch_count - l0
     skipped = overflowed()
+    first_window = None
     if skipped:                        # a skipped update is not a full step: measure again with the raised bound
+        first_window = {"ms_per_step": ms / args.steps, "skipped_updates": skipped}      # reported, not hidden
         l0 = capi.launch_count
-        ms = timed(resident_step, args.steps)
+        ms = timed(resident_step, args.steps, "resident (2nd window: the 1st had %d skipped update(s))" % skipped)
         launches = capi.launch_count - l0
         skipped = overflowed()
     for _ in range(2):
@@ -302,6 +375,7 @@ def run_ours(args):
     sampler.window(t_timed0, time.monotonic())
     clocks = sampler.stop()
     props_per_step = sharding.proposals_per_step(world, B_PER_GPU, N_PROP)
+    h2d_bytes = int(sum(bt["images_h"].numel() * 4 + bt["rois_h"].numel() * 4 for bt in batches) / len(batches))
     value = props_per_step * args.steps / (ms / 1e3)
     e2e_val = props_per_step * args.steps / (ms_e2e / 1e3)
 
@@ -368,7 +442,7 @@ def run_ours(args):
         roofline["timing"] = ("CUDA events around each launch on its stream, live inside %d resident steps "
                               "(WGRAD side-stream overlap off for these steps so durations are per kernel)" % prof_steps)
         for k in ("odwscl_roi_pool_fwd_nhwc_f32", "odwscl_roi_pool_bwd_nhwc_f32", "odwscl_roi_pool_bwd_nhwc_multi_f32",
-                  "odwscl_conv3x3_wgrad_nhwc_tf32", "odwscl_conv3x3_nhwc_tf32"):
+                  "odwscl_conv3x3_wgrad_nhwc_tf32", "odwscl_conv3x3_nhwc_tf32", "odwscl_fc_gemm_tf32"):
             if k != roofline["kernel"] and entry(k):
                 roofline[k.replace("odwscl_", "")] = entry(k)
 
@@ -400,19 +474,21 @@ def run_ours(args):
         return
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
-        rate, sec, cores = cpu_oracle_rate(args.cpu_sample_props)
+        rate, sec, cores = cpu_oracle_rate(min(args.cpu_sample_props, N_PROP))
         cpu_baseline = {"value": rate, "unit": "proposals/s", "cores": cores, "kind": "port",
-                        "sample": "oracle port: 1 image 1000x600, %d proposals, 1 fwd+bwd (%.1f s)" % (args.cpu_sample_props, sec)}
+                        "sample": "oracle port: 1 image %dx%d, %d proposals, 1 fwd+bwd (%.1f s)"
+                                  % (IMG_W, IMG_H, min(args.cpu_sample_props, N_PROP), sec)}
     line = {"metric": METRIC, "value": value, "unit": "proposals/s", "n_gpus": world, "steps": args.steps,
-            "warmup": n_warm, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": n_warm, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "fp32" if args.strict_fp32 else "fp32 storage, tf32 tensor-core conv/GEMM (the reference's torch-1.7.1 default); hand-written kernels fp32",
             "data": "synthetic",
             "config": {"workload": WORKLOAD,
                        "images_per_gpu": B_PER_GPU, "proposals_per_image": N_PROP, "parallelism": "dp%d" % world,
                        "host_syncs_per_step": 1 if args.sync_k else 0, "skipped_updates": [skipped, skipped_e2e],
+                       "calibration_steps": n_calib, "first_window_with_skipped_update": first_window,
                        "l2": "per-step working set (>=1.6 GB of activations) exceeds the 126 MB L2; kernel-alone timings flush L2 with a 256 MB write"},
             "e2e": {"value": e2e_val, "unit": "proposals/s", "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": int(images_h.numel() * 4 + rois_h.numel() * 4), "d2h_bytes_per_step": 8,
+                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8,
                     "redone_steps": redone[0]},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline}
     print(json.dumps(line), flush=True)
@@ -422,6 +498,7 @@ def run_ours(args):
 
 if __name__ == "__main__":
     a = parse()
+    a.scaling = apply_config(a.config, int(os.environ.get("WORLD_SIZE", "1")))
     if a.impl == "reference":
         run_reference(a)
     else:

@@ -219,5 +219,7 @@ def test_model_gradients_fused_activation_backward(capi):
     assert l1 == l0
     assert set(g1) == set(g0)
     for k in g0:
-        torch.testing.assert_close(g1[k], g0[k], rtol=2e-4, atol=2e-4 * float(g0[k].abs().max()) + 1e-12,
+        # (det_score.bias: its true gradient is 0 -- a softmax over proposals is shift-invariant -- what is left is
+        # summation-order noise ~1e-10, hence the absolute floor)
+        torch.testing.assert_close(g1[k], g0[k], rtol=2e-4, atol=2e-4 * float(g0[k].abs().max()) + 1e-8,
                                    msg=lambda m, k=k: k + ": " + m)
