@@ -192,7 +192,10 @@ int odwscl_conv_weight_xform_f32(const float* w_oihw, int Cout, int Cin, float* 
  *   ODWSCL_FC_MASK     x mask_scale where mask_src[m, n] > 0, else 0 (the ReLU+Dropout derivative of the layer below:
  *                      mask_src = its saved output, mask_scale = 1/(1-p))
  *   ODWSCL_FC_ROUND    round to TF32 (cvt.rna) -- for outputs another tensor-core GEMM consumes
- * max_pairs > 0 caps the resident CTA pairs (leave SMs to a concurrent NCCL all-reduce); 0 = all 74. */
+ * max_pairs > 0 caps the resident CTA pairs (leave SMs to a concurrent NCCL all-reduce); 0 = all 74.
+ * (A2, B2, K2 > 0): a second operand pair of the same majors whose contraction is appended to the first's,
+ * C = A B^T + A2 B2^T in ONE accumulation -- the weight gradient of a layer applied twice in a step (dW = dY1^T X1 +
+ * dY2^T X2: the [2R]-row batch and the augmented positives of loss.py:299-310) without a second gradient tensor. */
 #define ODWSCL_FC_BIAS 1
 #define ODWSCL_FC_ACCUM 2
 #define ODWSCL_FC_RELU 4
@@ -202,7 +205,7 @@ int odwscl_conv_weight_xform_f32(const float* w_oihw, int Cout, int Cin, float* 
 int odwscl_fc_gemm_tf32(const float* A, int lda, int a_mn_major, const float* B, int ldb, int b_mn_major, float* C,
                         int ldc, int M, int N, int K, int flags, const float* bias, const float* mask_src,
                         int ld_mask, float mask_scale, float dropout_p, unsigned long long seed, int max_pairs,
-                        odwscl_stream_t stream);
+                        const float* A2, int lda2, const float* B2, int ldb2, int K2, odwscl_stream_t stream);
 /* out[c] (+)= sum_r x[r, c] over a [rows, cols] matrix of pitch ld: the bias gradients of the block above
  * (accumulate != 0 adds to out, which folds a second call's gradient). */
 int odwscl_colsum_f32(const float* x, long long rows, int cols, int ld, float* out, int accumulate,

@@ -69,7 +69,8 @@ _SIGS = {
     "odwscl_relu_dropout_fwd_f32": (_I, [_P, ctypes.c_longlong, _F, ctypes.c_ulonglong, _P]),
     "odwscl_relu_dropout_bwd_f32": (_I, [_P, _P, _P, ctypes.c_longlong, _F, _P]),
     "odwscl_conv_weight_xform_f32": (_I, [_P, _I, _I, _P, _P, _I, _P]),
-    "odwscl_fc_gemm_tf32": (_I, [_P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P, _I, _F, _F, ctypes.c_ulonglong, _I, _P]),
+    "odwscl_fc_gemm_tf32": (_I, [_P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P, _I, _F, _F, ctypes.c_ulonglong, _I,
+                                 _P, _I, _P, _I, _I, _P]),
     "odwscl_colsum_f32": (_I, [_P, ctypes.c_longlong, _I, _I, _P, _I, _P]),
     "odwscl_head_scores_f32": (_I, [_P, _I, _I, _I, _I, _P, _I] + [_P] * 7 + [_P]),
     "odwscl_head_loss_f32": (_I, [_P, _I, _I, _I, _I, _I, _P, _I] + [_P] * 8 + [_F, _P, _P, _P, _P]),
@@ -129,7 +130,7 @@ _WORK = {
     # (A, B, C, M, N, K, ...)
     "odwscl_gemm_nt_tf32": lambda a: ("flop", 2.0 * a[3] * a[4] * a[5]),
     # (A, lda, a_mn, B, ldb, b_mn, C, ldc, M, N, K, ...)
-    "odwscl_fc_gemm_tf32": lambda a: ("flop", 2.0 * a[8] * a[9] * a[10]),
+    "odwscl_fc_gemm_tf32": lambda a: ("flop", 2.0 * a[8] * a[9] * (a[10] + a[23])),
 }
 
 
@@ -512,11 +513,18 @@ def _rows2d(t, name):
 
 
 def fc_gemm(A, B, a_mn=False, b_mn=False, out=None, bias=None, relu=False, dropout_p=0.0, seed=0, mask_src=None,
-            mask_scale=1.0, accumulate=False, round_tf32=False):
+            mask_scale=1.0, accumulate=False, round_tf32=False, A2=None, B2=None):
     """C[M,N] (+)= sum_k A(m,k) B(n,k) on the persistent tcgen05 CTA-pair kernel (TF32 math, fp32 accumulate).
     A: [M,K] (a_mn False) or [K,M] (a_mn True); B: [N,K] (b_mn False) or [K,N] (b_mn True); rows contiguous.
-    Fused epilogue: bias, accumulate, ReLU, Dropout(p, seed), derivative mask (mask_src > 0) * mask_scale, TF32 round."""
+    Fused epilogue: bias, accumulate, ReLU, Dropout(p, seed), derivative mask (mask_src > 0) * mask_scale, TF32 round.
+    (A2, B2): a second operand pair of the same layouts whose contraction is appended (C = A B^T + A2 B2^T)."""
     (A, lda), (B, ldb) = _rows2d(A, "A"), _rows2d(B, "B")
+    K2, lda2, ldb2 = 0, 0, 0
+    if A2 is not None:
+        (A2, lda2), (B2, ldb2) = _rows2d(A2, "A2"), _rows2d(B2, "B2")
+        K2 = A2.shape[0] if a_mn else A2.shape[1]
+        assert (A2.shape[1] if a_mn else A2.shape[0]) == (A.shape[1] if a_mn else A.shape[0])
+        assert (B2.shape[0] if b_mn else B2.shape[1]) == K2 and (B2.shape[1] if b_mn else B2.shape[0]) == (B.shape[1] if b_mn else B.shape[0])
     K, M = (A.shape[0], A.shape[1]) if a_mn else (A.shape[1], A.shape[0])
     Kb, N = (B.shape[0], B.shape[1]) if b_mn else (B.shape[1], B.shape[0])
     if K != Kb:
@@ -556,7 +564,8 @@ def fc_gemm(A, B, a_mn=False, b_mn=False, out=None, bias=None, relu=False, dropo
     with torch.cuda.device(A.device):
         _call("odwscl_fc_gemm_tf32", _ptr(A), int(lda), int(a_mn), _ptr(B), int(ldb), int(b_mn), _ptr(out), int(ldc), M, N,
               K, flags, _ptr(bias), _ptr(mask_src), int(ld_mask), float(mask_scale), float(dropout_p),
-              ctypes.c_ulonglong(seed & (2 ** 64 - 1)), int(FC_MAX_PAIRS), _stream())
+              ctypes.c_ulonglong(seed & (2 ** 64 - 1)), int(FC_MAX_PAIRS), _ptr(A2) if K2 else None, int(lda2),
+              _ptr(B2) if K2 else None, int(ldb2), int(K2), _stream())
     return out
 
 

@@ -77,7 +77,8 @@ struct FcEpi {
 
 struct FcSk {
   int m_tiles, n_tiles;     // 256-row / 256-column pair tiles
-  int n_ptiles, kiters;
+  int n_ptiles, kiters;     // kiters = kiters0 + the 32-wide K steps of the optional second operand pair
+  int kiters0;              // K steps served by the first (A, B) pair
   int np, rounds, left, slices;
   int panel;                // n-tiles per raster panel
   float* ws;                // [left * slices][2][128][256] partial accumulators
@@ -117,35 +118,20 @@ __device__ __forceinline__ void fc_tile_coords(const FcSk& sk, int pt, int& m0, 
   n0 = nt * kBN;
 }
 
-// 32 consecutive output columns of one row: the fused epilogue
-__device__ __forceinline__ void fc_epilogue_store(float (&v)[32], float* __restrict__ C, int ldc, int row, int col, int M, int N,
-                                                  const FcEpi& ep) {
-  if (row >= M || col >= N) return;
+// Fused epilogue of one 32-row x 32-column chunk, warp-cooperative.  On entry lane = accumulator row (v[] = 32 consecutive
+// columns of row row0 + lane, as tcgen05.ld delivers them).  The chunk is transposed through shared memory (33-float pitch:
+// conflict-free both ways) so that every global access -- the store, the accumulate read, the derivative-mask read -- is a
+// full 128-byte row segment per warp instruction instead of 32 scattered 16-byte pieces.  The Dropout bits are drawn in the
+// row domain (one Philox call covers 8 consecutive columns of a row) and travel as a 32-bit keep mask per row.
+__device__ __forceinline__ void fc_epilogue_store(float (&v)[32], float* __restrict__ sbuf, float* __restrict__ C, int ldc,
+                                                  int row0, int col0, int M, int N, const FcEpi& ep, int lane) {
+  if (row0 >= M || col0 >= N) return;                       // warp-uniform
   const int flags = ep.flags;
-  const bool full = (col + 32 <= N) && ((ldc & 3) == 0);
-  float* dst = C + (size_t)row * ldc + col;
-  if (flags & kBias) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) if (col + j < N) v[j] += __ldg(ep.bias + col + j);
-  }
-  if (flags & kAccum) {
-    if (full) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 p = reinterpret_cast<const float4*>(dst)[j];
-        v[4 * j] += p.x; v[4 * j + 1] += p.y; v[4 * j + 2] += p.z; v[4 * j + 3] += p.w;
-      }
-    } else {
-      for (int j = 0; j < 32 && col + j < N; ++j) v[j] += dst[j];
-    }
-  }
-  if (flags & kRelu) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-  }
-  if (flags & kDropout) {
-    // element (row, col + j): 16 random bits of Philox(seed, counter = (row * N + col + j) / 8), lane (.. % 8)
-    const unsigned long long e0 = (unsigned long long)row * (unsigned long long)N + (unsigned long long)col;
+  uint32_t keep = 0xFFFFFFFFu;
+  if ((flags & kDropout) && row0 + lane < M) {
+    // element (row, col): 16 random bits of Philox(seed, counter = (row * N + col) / 8), slot (row * N + col) % 8
+    const unsigned long long e0 = (unsigned long long)(row0 + lane) * (unsigned long long)N + (unsigned long long)col0;
+    keep = 0u;
     if ((e0 & 7ull) == 0) {
 #pragma unroll
       for (int c4 = 0; c4 < 4; ++c4) {
@@ -154,51 +140,48 @@ __device__ __forceinline__ void fc_epilogue_store(float (&v)[32], float* __restr
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
           const uint32_t bits = (r[t >> 1] >> ((t & 1) * 16)) & 0xFFFFu;
-          v[c4 * 8 + t] = bits >= ep.drop_thr16 ? v[c4 * 8 + t] * ep.drop_scale : 0.f;
+          keep |= (bits >= ep.drop_thr16 ? 1u : 0u) << (c4 * 8 + t);
         }
       }
-    } else {                                   // N % 8 != 0: per-element counters (never on the fc6 / fc7 shapes)
+    } else {                                                // N % 8 != 0: per-element counters (never on the fc6 / fc7 shapes)
       for (int j = 0; j < 32; ++j) {
         uint32_t r[4];
         const unsigned long long e = e0 + j;
         philox4x32_10(ep.seed, e >> 3, r);
         const int t = (int)(e & 7ull);
         const uint32_t bits = (r[t >> 1] >> ((t & 1) * 16)) & 0xFFFFu;
-        v[j] = bits >= ep.drop_thr16 ? v[j] * ep.drop_scale : 0.f;
+        keep |= (bits >= ep.drop_thr16 ? 1u : 0u) << j;
       }
     }
   }
-  if (flags & kMask) {
-    const float* ms = ep.mask_src + (size_t)row * ep.ld_mask + col;
-    if (full && (ep.ld_mask & 3) == 0) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 mm = __ldg(reinterpret_cast<const float4*>(ms) + j);
-        v[4 * j] = mm.x > 0.f ? v[4 * j] * ep.mask_scale : 0.f;
-        v[4 * j + 1] = mm.y > 0.f ? v[4 * j + 1] * ep.mask_scale : 0.f;
-        v[4 * j + 2] = mm.z > 0.f ? v[4 * j + 2] * ep.mask_scale : 0.f;
-        v[4 * j + 3] = mm.w > 0.f ? v[4 * j + 3] * ep.mask_scale : 0.f;
-      }
-    } else {
-      for (int j = 0; j < 32 && col + j < N; ++j) v[j] = __ldg(ms + j) > 0.f ? v[j] * ep.mask_scale : 0.f;
+  for (int j = 0; j < 32; ++j) sbuf[lane * 33 + j] = v[j];
+  __syncwarp();
+  const int col = col0 + lane;
+  const bool colok = col < N;
+  const float bias = ((flags & kBias) && colok) ? __ldg(ep.bias + col) : 0.f;
+  const int nrows = min(32, M - row0);
+#pragma unroll 4
+  for (int rr = 0; rr < nrows; ++rr) {
+    float x = sbuf[rr * 33 + lane] + bias;
+    const uint32_t kb = (flags & kDropout) ? __shfl_sync(0xFFFFFFFFu, keep, rr) : 0xFFFFFFFFu;
+    if (colok) {
+      float* dst = C + (size_t)(row0 + rr) * ldc + col;
+      if (flags & kAccum) x += *dst;
+      if (flags & kRelu) x = fmaxf(x, 0.f);
+      if (flags & kDropout) x = ((kb >> lane) & 1u) ? x * ep.drop_scale : 0.f;
+      if (flags & kMask) x = __ldg(ep.mask_src + (size_t)(row0 + rr) * ep.ld_mask + col) > 0.f ? x * ep.mask_scale : 0.f;
+      if (flags & kRound) x = rna_tf32(x);
+      *dst = x;
     }
   }
-  if (flags & kRound) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = rna_tf32(v[j]);
-  }
-  if (full) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-  } else {
-    for (int j = 0; j < 32 && col + j < N; ++j) dst[j] = v[j];
-  }
+  __syncwarp();                                             // the next chunk reuses sbuf
 }
 
 template <bool AMN, bool BMN>
 __global__ void __launch_bounds__(192, 1)
 fc_gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                         const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_b1,
                          float* __restrict__ C, int M, int N, int ldc, const FcEpi ep, const FcSk sk) {
   constexpr int A_BYTES = kBM * tc::kTileKBytes, B_BYTES = (kBN / 2) * tc::kTileKBytes;    // 16 KB + 16 KB per CTA
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -206,6 +189,7 @@ fc_gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_s;
+  __shared__ float epi_buf[4][32 * 33];                        // per epilogue warp: transposition buffer of one chunk
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = tc::cluster_ctarank();
@@ -214,6 +198,7 @@ fc_gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
   if (warp == 0 && tc::elect_one()) {
     tc::tma_prefetch_desc(&map_a);
     tc::tma_prefetch_desc(&map_b);
+    if (sk.kiters0 < sk.kiters) { tc::tma_prefetch_desc(&map_a1); tc::tma_prefetch_desc(&map_b1); }
     for (int s = 0; s < kStages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&tmem_full_bar[i], 1); tc::mbar_init(&tmem_empty_bar[i], 256); }
     tc::fence_barrier_init();
@@ -240,18 +225,23 @@ fc_gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
           tc::mbar_wait(&empty_bar[s], ((it / kStages) & 1) ^ 1);
           if (crank == 0) tc::mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
           uint8_t* a = tiles + (size_t)s * STAGE_BYTES;
-          const int k0 = kk * tc::kTileK;
+          // the contraction runs over the K steps of the first operand pair, then over those of the second (two calls
+          // of one layer folded into a single weight-gradient GEMM); each pair has its own bounds (zero fill)
+          const bool second = kk >= sk.kiters0;
+          const CUtensorMap* ma = second ? &map_a1 : &map_a;
+          const CUtensorMap* mb = second ? &map_b1 : &map_b;
+          const int k0 = (second ? kk - sk.kiters0 : kk) * tc::kTileK;
           if (AMN) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) tc::tma_load_2d_2sm(a + j * kBox, &map_a, &full_bar[s], am0 + 32 * j, k0);
+            for (int j = 0; j < 4; ++j) tc::tma_load_2d_2sm(a + j * kBox, ma, &full_bar[s], am0 + 32 * j, k0);
           } else {
-            tc::tma_load_2d_2sm(a, &map_a, &full_bar[s], k0, am0);
+            tc::tma_load_2d_2sm(a, ma, &full_bar[s], k0, am0);
           }
           if (BMN) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) tc::tma_load_2d_2sm(a + A_BYTES + j * kBox, &map_b, &full_bar[s], bn0 + 32 * j, k0);
+            for (int j = 0; j < 4; ++j) tc::tma_load_2d_2sm(a + A_BYTES + j * kBox, mb, &full_bar[s], bn0 + 32 * j, k0);
           } else {
-            tc::tma_load_2d_2sm(a + A_BYTES, &map_b, &full_bar[s], k0, bn0);
+            tc::tma_load_2d_2sm(a + A_BYTES, mb, &full_bar[s], k0, bn0);
           }
         }
       }
@@ -295,7 +285,7 @@ fc_gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
       const int buf = item & 1;
       int m0, n0;
       fc_tile_coords(sk, wi.tile, m0, n0);
-      const int row = m0 + (int)crank * kBM + trow;
+      const int row0 = m0 + (int)crank * kBM + q * 32;          // first row of this warp's 32 accumulator rows
       tc::mbar_wait(&tmem_full_bar[buf], (item >> 1) & 1);
       tc::tc_fence_after();
       if (wi.left_idx < 0) {
@@ -303,7 +293,7 @@ fc_gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         for (int c = 0; c < kBN / 32; ++c) {
           tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * kBN + c * 32, v);
           tc::tmem_ld_wait();
-          fc_epilogue_store(v, C, ldc, row, n0 + c * 32, M, N, ep);
+          fc_epilogue_store(v, epi_buf[q], C, ldc, row0, n0 + c * 32, M, N, ep, lane);
         }
         tc::tc_fence_before();
         tc::mbar_arrive_leader(&tmem_empty_bar[buf]);
@@ -329,7 +319,7 @@ fc_gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     if (fc_item(sk, pair, 0, wi) && wi.left_idx >= 0) {
       int m0, n0;
       fc_tile_coords(sk, wi.tile, m0, n0);
-      const int row = m0 + (int)crank * kBM + trow;
+      const int row0 = m0 + (int)crank * kBM + q * 32;
       const int* counter = sk.flags + wi.left_idx * 2 + crank;
       while (*reinterpret_cast<const volatile int*>(counter) < sk.slices) __nanosleep(64);
       __threadfence();
@@ -345,7 +335,7 @@ fc_gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             v[4 * j] += p.x; v[4 * j + 1] += p.y; v[4 * j + 2] += p.z; v[4 * j + 3] += p.w;
           }
         }
-        fc_epilogue_store(v, C, ldc, row, n0 + ch * 32, M, N, ep);
+        fc_epilogue_store(v, epi_buf[q], C, ldc, row0, n0 + ch * 32, M, N, ep, lane);
       }
     }
   }
@@ -377,14 +367,23 @@ int make_operand_map(CUtensorMap* map, const float* p, int rows, int K, int ld, 
   return tc::make_tmap_f32(map, p, 2, d, s, b);
 }
 
+struct FcOperands { const float* A; int lda; const float* B; int ldb; int K; };
+
 template <bool AMN, bool BMN>
-int launch_fc(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K, const FcEpi& ep,
+int launch_fc(const FcOperands& o0, const FcOperands& o1, float* C, int ldc, int M, int N, const FcEpi& ep,
               int max_pairs_cap, cudaStream_t st) {
-  CUtensorMap ma, mb;
-  int rc = make_operand_map(&ma, A, M, K, lda, AMN);
+  CUtensorMap ma, mb, ma1, mb1;
+  int rc = make_operand_map(&ma, o0.A, M, o0.K, o0.lda, AMN);
   if (rc) return rc;
-  rc = make_operand_map(&mb, B, N, K, ldb, BMN);
+  rc = make_operand_map(&mb, o0.B, N, o0.K, o0.ldb, BMN);
   if (rc) return rc;
+  ma1 = ma; mb1 = mb;
+  if (o1.K > 0) {
+    rc = make_operand_map(&ma1, o1.A, M, o1.K, o1.lda, AMN);
+    if (rc) return rc;
+    rc = make_operand_map(&mb1, o1.B, N, o1.K, o1.ldb, BMN);
+    if (rc) return rc;
+  }
   constexpr int smem = kStages * (kBM + kBN / 2) * tc::kTileKBytes + 1024;
   auto kern = fc_gemm_tf32_2cta_kernel<AMN, BMN>;
   ODW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -410,7 +409,8 @@ int launch_fc(const float* A, int lda, const float* B, int ldb, float* C, int ld
   sk.m_tiles = odw_cdiv(M, 2 * kBM);
   sk.n_tiles = odw_cdiv(N, kBN);
   sk.n_ptiles = sk.m_tiles * sk.n_tiles;
-  sk.kiters = odw_cdiv(K, tc::kTileK);
+  sk.kiters0 = odw_cdiv(o0.K, tc::kTileK);
+  sk.kiters = sk.kiters0 + (o1.K > 0 ? odw_cdiv(o1.K, tc::kTileK) : 0);
   sk.panel = min(sk.n_tiles, 8);
   int cap = min(max_pairs, ODW_NUM_SMS / 2);
   if (max_pairs_cap > 0) cap = min(cap, max_pairs_cap);
@@ -442,7 +442,7 @@ int launch_fc(const float* A, int lda, const float* B, int ldb, float* C, int ld
   sk.flags = reinterpret_cast<int*>(reinterpret_cast<char*>(g_fc_ws) + ws_floats * sizeof(float));
   if (sk.left > 0) ODW_CUDA(cudaMemsetAsync(sk.flags, 0, (size_t)(sk.left + 1) * 2 * sizeof(int), st));
   cfg.gridDim = dim3(2 * sk.np);
-  ODW_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, C, M, N, ldc, ep, sk));
+  ODW_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, ma1, mb1, C, M, N, ldc, ep, sk));
   return 0;
 }
 
@@ -470,8 +470,8 @@ colsum_kernel(const float* __restrict__ x, long long rows, int cols, int ld, flo
 ODW_API int odwscl_fc_gemm_tf32(const float* A, int lda, int a_mn_major, const float* B, int ldb, int b_mn_major, float* C,
                                 int ldc, int M, int N, int K, int flags, const float* bias, const float* mask_src,
                                 int ld_mask, float mask_scale, float dropout_p, unsigned long long seed, int max_pairs,
-                                odwscl_stream_t stream) {
-  if (M < 0 || N < 0 || K < 0 || lda <= 0 || ldb <= 0 || ldc < N) return ODWSCL_EINVAL;
+                                const float* A2, int lda2, const float* B2, int ldb2, int K2, odwscl_stream_t stream) {
+  if (M < 0 || N < 0 || K < 0 || K2 < 0 || lda <= 0 || ldb <= 0 || ldc < N) return ODWSCL_EINVAL;
   if ((lda & 3) || (ldb & 3)) return ODWSCL_EINVAL;                      // TMA: 16-byte row pitch
   if (a_mn_major ? lda < M : lda < K) return ODWSCL_EINVAL;
   if (b_mn_major ? ldb < N : ldb < K) return ODWSCL_EINVAL;
@@ -479,6 +479,10 @@ ODW_API int odwscl_fc_gemm_tf32(const float* A, int lda, int a_mn_major, const f
   if (M == 0 || N == 0) return 0;
   if (!A || !B || !C || K == 0) return ODWSCL_EINVAL;
   if (((uintptr_t)A & 15) || ((uintptr_t)B & 15) || ((uintptr_t)C & 15) || ((uintptr_t)mask_src & 15)) return ODWSCL_EINVAL;
+  if (K2 > 0) {
+    if (!A2 || !B2 || (lda2 & 3) || (ldb2 & 3) || ((uintptr_t)A2 & 15) || ((uintptr_t)B2 & 15)) return ODWSCL_EINVAL;
+    if ((a_mn_major ? lda2 < M : lda2 < K2) || (b_mn_major ? ldb2 < N : ldb2 < K2)) return ODWSCL_EINVAL;
+  }
   if ((flags & kBias) && !bias) return ODWSCL_EINVAL;
   if ((flags & kMask) && (!mask_src || ld_mask < N)) return ODWSCL_EINVAL;
   FcEpi ep;
@@ -487,10 +491,11 @@ ODW_API int odwscl_fc_gemm_tf32(const float* A, int lda, int a_mn_major, const f
   ep.drop_thr16 = (uint32_t)(dropout_p * 65536.0f);
   ep.seed = seed; ep.flags = flags;
   cudaStream_t st = (cudaStream_t)stream;
-  if (!a_mn_major && !b_mn_major) return launch_fc<false, false>(A, lda, B, ldb, C, ldc, M, N, K, ep, max_pairs, st);
-  if (!a_mn_major && b_mn_major) return launch_fc<false, true>(A, lda, B, ldb, C, ldc, M, N, K, ep, max_pairs, st);
-  if (a_mn_major && b_mn_major) return launch_fc<true, true>(A, lda, B, ldb, C, ldc, M, N, K, ep, max_pairs, st);
-  return launch_fc<true, false>(A, lda, B, ldb, C, ldc, M, N, K, ep, max_pairs, st);
+  const FcOperands o0{A, lda, B, ldb, K}, o1{A2, lda2, B2, ldb2, K2};
+  if (!a_mn_major && !b_mn_major) return launch_fc<false, false>(o0, o1, C, ldc, M, N, ep, max_pairs, st);
+  if (!a_mn_major && b_mn_major) return launch_fc<false, true>(o0, o1, C, ldc, M, N, ep, max_pairs, st);
+  if (a_mn_major && b_mn_major) return launch_fc<true, true>(o0, o1, C, ldc, M, N, ep, max_pairs, st);
+  return launch_fc<true, false>(o0, o1, C, ldc, M, N, ep, max_pairs, st);
 }
 
 ODW_API int odwscl_colsum_f32(const float* x, long long rows, int cols, int ld, float* out, int accumulate,

@@ -107,16 +107,21 @@ class _LinearFn(Function):
             st.setdefault("pending", []).append((dz, x))
             return (gx,) + (None,) * 11
         gw = gb = None
+        pend = st.pop("pending", []) if (ctx.role == "main" and st is not None) else []
         if need_w:
-            gw = _gemm(dz, x, ctx.strict, a_mn=True, b_mn=True)
+            if len(pend) == 1 and not ctx.strict:
+                # the small call's (dZ, x) ride in the same accumulation as a second operand pair: one GEMM, one tensor
+                gw = capi.fc_gemm(dz, x, a_mn=True, b_mn=True, A2=pend[0][0], B2=pend[0][1])
+            else:
+                gw = _gemm(dz, x, ctx.strict, a_mn=True, b_mn=True)
+                for dzs, xs in pend:
+                    _gemm(dzs, xs, ctx.strict, a_mn=True, b_mn=True, out=gw, accumulate=True)
             if ctx.has_bias:
                 gb = capi.colsum(dz)
-            if ctx.role == "main" and st is not None:
-                for dzs, xs in st.pop("pending", []):
-                    _gemm(dzs, xs, ctx.strict, a_mn=True, b_mn=True, out=gw, accumulate=True)
-                    if gb is not None:
-                        capi.colsum(dzs, out=gb, accumulate=True)
-                st["main_done"] = True
+                for dzs, _ in pend:
+                    capi.colsum(dzs, out=gb, accumulate=True)
+        if ctx.role == "main" and st is not None:
+            st["main_done"] = True
         return (gx, gw, gb) + (None,) * 9
 
 

@@ -187,8 +187,11 @@ class RoIRegLossComputation(object):
         ReLU/Dropout derivative rides in Sim_Net's dgrad epilogue (fc.linear in_mask_scale) when the extractor supports it."""
         scale = getattr(feature_extractor, "out_act_scale", None)
         from . import fc
-        if scale is not None and fc.FUSE_ACT_BWD and torch.is_grad_enabled():
-            return model_sim(feature_extractor.forward_neck(aug, fuse_out_bwd=True), in_mask_scale=scale())
+        if scale is not None:                                   # the product's extractor + Sim_Net
+            role = "small" if getattr(model_sim, "_stash", None) is not None else None
+            if fc.FUSE_ACT_BWD and torch.is_grad_enabled():
+                return model_sim(feature_extractor.forward_neck(aug, fuse_out_bwd=True), in_mask_scale=scale(), role=role)
+            return model_sim(feature_extractor.forward_neck(aug), role=role)
         return model_sim(feature_extractor.forward_neck(aug))
 
     def _augmented_positives_synced(self, st, P, clean_pooled_feats, feature_extractor, model_sim):

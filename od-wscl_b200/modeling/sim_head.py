@@ -22,14 +22,21 @@ class Sim_Net(nn.Module):
 
         self.strict_fp32 = False       # True: 3xTF32 split products (parity tests)
 
-    def forward(self, roi_feat, in_mask_scale=None):
-        """in_mask_scale: roi_feat comes from run_classifier(..., fuse_out_bwd=True) and this is its only consumer."""
+    def forward(self, roi_feat, in_mask_scale=None, role=None):
+        """in_mask_scale: roi_feat comes from run_classifier(..., fuse_out_bwd=True) and this is its only consumer.
+        role: "main" (all proposals, weak_head.py:110) / "small" (augmented positives, loss.py:301,305) -- the weight
+        gradients of the two calls of a training step are produced as one tensor per layer (fc._LinearFn)."""
         from . import fc
         fuse = fc.FUSE_ACT_BWD and torch.is_grad_enabled()
+        if role == "main":
+            self._stash = {"mlp0": {}, "mlp2": {}}
+        st = getattr(self, "_stash", None) if role is not None else None
         h = fc.linear(roi_feat, self.mlp[0].weight, self.mlp[0].bias, act=fc.ACT_RELU, round_out=True,
-                      strict=self.strict_fp32, in_mask_scale=in_mask_scale, act_bwd_fused=fuse)
+                      strict=self.strict_fp32, in_mask_scale=in_mask_scale, act_bwd_fused=fuse,
+                      stash=st["mlp0"] if st is not None else None, role=role if st is not None else None)
         return F.normalize(fc.linear(h, self.mlp[2].weight, self.mlp[2].bias, strict=self.strict_fp32,
-                                     in_mask_scale=1.0 if fuse else None), dim=1)
+                                     in_mask_scale=1.0 if fuse else None, stash=st["mlp2"] if st is not None else None,
+                                     role=role if st is not None else None), dim=1)
 
 
 class _SupConBankFn(Function):

@@ -91,7 +91,7 @@ class VGG16FC67ROIFeatureExtractor(nn.Module):
         self.sim_drop = DropBlock2D(block_size=1, drop_prob=0.3)
         self.noise_sampler = None      # test hook: callable(shape, device) -> N(0,1) tensor
         self.strict_fp32 = False       # True: every fc product as a 3xTF32 split (parity tests)
-        self.merge_fc6_wgrad = True    # train: the two fc6 weight gradients of a step leave as one tensor (_Fc6Fn)
+        self.merge_fc6_wgrad = True    # train: the weight gradients of the two fc6 / fc7 calls of a step leave as one tensor each
         self._fc6_stash = None
         self.fuse_clean_aug = True     # train: ROIPool + DropBlock into one [2R,...] batch, fc6/fc7 once
         if init_weights:
@@ -109,15 +109,17 @@ class VGG16FC67ROIFeatureExtractor(nn.Module):
         (fc.linear(..., in_mask_scale=self.out_act_scale())), so no separate elementwise backward pass is left."""
         from . import fc
         c = self.classifier
-        stash = self._fc6_stash if (role is not None and self.merge_fc6_wgrad) else None
+        stash = self._fc6_stash if (role is not None and self.merge_fc6_wgrad) else None     # {"fc6": {}, "fc7": {}}
         fuse = fc.FUSE_ACT_BWD and torch.is_grad_enabled()
         p6 = float(c[3].p) if self.training else 0.0
         p7 = float(c[6].p) if self.training else 0.0
         x = fc.linear(x, c[1].weight, c[1].bias, act=fc.ACT_RELU_DROPOUT if p6 > 0.0 else fc.ACT_RELU, p=p6,
-                      seed=fc.next_dropout_seed() if p6 > 0.0 else 0, round_out=True, strict=self.strict_fp32, stash=stash,
-                      role=role if stash is not None else None, act_bwd_fused=fuse)
+                      seed=fc.next_dropout_seed() if p6 > 0.0 else 0, round_out=True, strict=self.strict_fp32,
+                      stash=stash["fc6"] if stash is not None else None, role=role if stash is not None else None,
+                      act_bwd_fused=fuse)
         x = fc.linear(x, c[4].weight, c[4].bias, act=fc.ACT_RELU_DROPOUT if p7 > 0.0 else fc.ACT_RELU, p=p7,
                       seed=fc.next_dropout_seed() if p7 > 0.0 else 0, round_out=True, strict=self.strict_fp32,
+                      stash=stash["fc7"] if stash is not None else None, role=role if stash is not None else None,
                       in_mask_scale=1.0 / (1.0 - p6) if fuse else None, act_bwd_fused=fuse and fuse_out_bwd)
         return x
 
@@ -153,7 +155,8 @@ class VGG16FC67ROIFeatureExtractor(nn.Module):
             centres = (torch.rand(R, ph, pw, device=rois.device) < gamma).float()
         stash = {}
         buf = pool_and_augment(x[0].float(), rois, (ph, pw), pool.spatial_scale, centres.contiguous(), db.block_size, stash)
-        self._fc6_stash = {} if self.merge_fc6_wgrad else None      # one stash per step: main call here, small calls later
+        # one stash per layer and step: the main call here, the small (augmented positives) calls later
+        self._fc6_stash = {"fc6": {}, "fc7": {}} if self.merge_fc6_wgrad else None
         feats = self.run_classifier(buf.view(2 * R, -1), role="main" if self._fc6_stash is not None else None,
                                     fuse_out_bwd=fuse_out_bwd)
         clean, aug = split_rows(feats, R)

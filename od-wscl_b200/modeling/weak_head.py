@@ -34,6 +34,7 @@ class ROIWeakRegHead(nn.Module):
 
     def forward(self, features, proposals, targets=None, model_cdb=None, iteration=None):
         fe = self.feature_extractor
+        self.model_sim._stash = None             # per-step state of the two-call weight-gradient fold (fc._LinearFn)
         if self.training and self.DB_METHOD == "dropblock" and getattr(fe, "can_fuse_clean_aug", lambda: False)():
             # :107 and :111-112 as ONE fc6/fc7 batch over [clean; DropBlock-augmented] pooled features
             # each half of the fc7 output has exactly one consumer, whose dgrad epilogue applies fc7's ReLU/Dropout mask
@@ -42,7 +43,7 @@ class ROIWeakRegHead(nn.Module):
             clean_roi_feats, aug_roi_feats, clean_pooled_feats = fe.forward_clean_and_aug(features, proposals,
                                                                                           fuse_out_bwd=fuse)
             s7 = fe.out_act_scale() if fuse else None
-            sim_feature = self.model_sim(clean_roi_feats, in_mask_scale=s7)                           # :110
+            sim_feature = self.model_sim(clean_roi_feats, in_mask_scale=s7, role="main")              # :110
             cls_score, det_score, ref_scores, ref_bbox_preds = self.predictor(aug_roi_feats, proposals,
                                                                               in_mask_scale=s7)       # :113
             loss_img, accuracy_img = self.loss_evaluator([cls_score], [det_score], ref_scores, ref_bbox_preds,

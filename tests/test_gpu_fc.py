@@ -223,3 +223,16 @@ def test_model_gradients_fused_activation_backward(capi):
         # summation-order noise ~1e-10, hence the absolute floor)
         torch.testing.assert_close(g1[k], g0[k], rtol=2e-4, atol=2e-4 * float(g0[k].abs().max()) + 1e-8,
                                    msg=lambda m, k=k: k + ": " + m)
+
+
+def test_fc_gemm_second_operand_pair(capi):
+    """C = A B^T + A2 B2^T in one accumulation (K-concatenated operand pairs), every layout the block uses."""
+    g = torch.Generator().manual_seed(8)
+    M, N, K1, K2 = 300, 520, 1000, 77
+    A, B = _q(torch.randn(M, K1, generator=g)), _q(torch.randn(N, K1, generator=g))
+    A2, B2 = _q(torch.randn(M, K2, generator=g)), _q(torch.randn(N, K2, generator=g))
+    ref = (A.double() @ B.double().T + A2.double() @ B2.double().T).float()
+    for a_mn, b_mn in ((True, True), (False, False), (False, True)):
+        f = lambda t, mn: (t.T.contiguous() if mn else t).cuda()
+        got = capi.fc_gemm(f(A, a_mn), f(B, b_mn), a_mn=a_mn, b_mn=b_mn, A2=f(A2, a_mn), B2=f(B2, b_mn)).cpu()
+        torch.testing.assert_close(got, ref, rtol=1e-6, atol=2e-5 * (K1 + K2) ** 0.5)
