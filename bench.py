@@ -181,6 +181,82 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------ stock-PyTorch GPU arm
+def run_stock_gpu(args):
+    """`--impl stock-gpu`: the stand-in for "the reference's own GPU build" north_star's >= 1.5x target is quoted
+    against (oracle/stock_gpu.py: the reference's op sequence and host synchronisations on stock torch / torchvision
+    CUDA ops -- cuDNN, cuBLAS, torchvision roi_pool + nms, TF32 on).  Bench-side only; nothing of the product runs here.
+    Same synthetic inputs, config, optimizer settings and timing protocol as our arm; one GPU."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    try:
+        import torchvision  # noqa: F401
+        from oracle import oracle as orc, stock_gpu
+        assert torch.cuda.is_available()
+        dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+        torch.ops.torchvision.roi_pool(torch.zeros(1, 1, 8, 8, device=dev), torch.tensor([[0., 0, 0, 7, 7]], device=dev), 1.0, 2, 2)
+    except Exception as e:
+        print(json.dumps({"impl": "stock-gpu", "unavailable": "%s: %s" % (type(e).__name__, str(e)[:160])}), flush=True)
+        return
+    torch.cuda.set_device(dev)
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cudnn.benchmark = True
+    torch.manual_seed(0)
+    sd = {k: v.to(dev).requires_grad_(not k.split(".")[3] in ("0", "2", "5", "7") if k.startswith("backbone") else True)
+          for k, v in orc.synth_state_dict(NUM_CLASSES, seed=0).items()}
+    wts = [v for k, v in sd.items() if v.requires_grad and "bias" not in k]
+    bia = [v for k, v in sd.items() if v.requires_grad and "bias" in k]
+    opt = torch.optim.SGD([{"params": wts, "lr": 0.01, "weight_decay": 0.0001},
+                           {"params": bia, "lr": 0.02, "weight_decay": 0.0}], lr=0.01, momentum=0.9)
+    images_h, boxes_h, labels = orc.synth_batch(B_PER_GPU, N_PROP, IMG_W, IMG_H, NUM_CLASSES, seed=1234)
+    images_h = images_h.pin_memory()
+    boxes_h = [b.pin_memory() for b in boxes_h]
+    images_d, boxes_d = images_h.to(dev), [b.to(dev) for b in boxes_h]
+
+    def step(images, boxes):
+        losses = stock_gpu.train_step(sd, images, boxes, labels)
+        total = sum(losses.values())
+        opt.zero_grad(set_to_none=True)
+        total.backward()
+        opt.step()
+        return total
+
+    def timed(fn, n):
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b)
+    for _ in range(max(args.warmup, 3)):
+        step(images_d, boxes_d)
+    ms = timed(lambda: step(images_d, boxes_d), args.steps)
+    loss_h = torch.zeros(1).pin_memory()
+
+    def e2e():
+        total = step(images_h.to(dev, non_blocking=True), [b.to(dev, non_blocking=True) for b in boxes_h])
+        loss_h.copy_(total.detach().view(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    e2e()
+    ms_e2e = timed(e2e, args.steps)
+    n = B_PER_GPU * N_PROP
+    line = {"impl": "stock-gpu", "metric": METRIC, "value": n * args.steps / (ms / 1e3), "unit": "proposals/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "fp32 storage, tf32 cuDNN / cuBLAS", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "images_per_gpu": B_PER_GPU, "proposals_per_image": N_PROP,
+                       "what": "oracle/stock_gpu.py: the reference's op sequence + host syncs on stock torch/torchvision CUDA ops"},
+            "e2e": {"value": n * args.steps / (ms_e2e / 1e3), "unit": "proposals/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": int(images_h.numel() * 4 + sum(b.numel() for b in boxes_h) * 4),
+                    "d2h_bytes_per_step": 4},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
 # ------------------------------------------------------------------------------ GPU arm
 def make_optimizer(model):
     """solver/build.py:10-24: SGD, bias lr x2 and no weight decay on biases."""
@@ -501,5 +577,7 @@ if __name__ == "__main__":
     a.scaling = apply_config(a.config, int(os.environ.get("WORLD_SIZE", "1")))
     if a.impl == "reference":
         run_reference(a)
+    elif a.impl == "stock-gpu":
+        run_stock_gpu(a)
     else:
         run_ours(a)

@@ -37,7 +37,6 @@ namespace {
 
 constexpr int kBM = 128;                 // rows of A per CTA (256 per pair)
 constexpr int kBN = 256;                 // columns per pair tile
-constexpr int kStages = 6;
 constexpr int kBox = 32 * 128;           // bytes of one MN-major {32 rows(mn) x 32 k} TMA box
 enum : int { kBias = 1, kAccum = 2, kRelu = 4, kDropout = 8, kMask = 16, kRound = 32 };
 
@@ -118,20 +117,38 @@ __device__ __forceinline__ void fc_tile_coords(const FcSk& sk, int pt, int& m0, 
   n0 = nt * kBN;
 }
 
-// Fused epilogue of one 32-row x 32-column chunk, warp-cooperative.  On entry lane = accumulator row (v[] = 32 consecutive
-// columns of row row0 + lane, as tcgen05.ld delivers them).  The chunk is transposed through shared memory (33-float pitch:
-// conflict-free both ways) so that every global access -- the store, the accumulate read, the derivative-mask read -- is a
-// full 128-byte row segment per warp instruction instead of 32 scattered 16-byte pieces.  The Dropout bits are drawn in the
-// row domain (one Philox call covers 8 consecutive columns of a row) and travel as a 32-bit keep mask per row.
-__device__ __forceinline__ void fc_epilogue_store(float (&v)[32], float* __restrict__ sbuf, float* __restrict__ C, int ldc,
-                                                  int row0, int col0, int M, int N, const FcEpi& ep, int lane) {
-  if (row0 >= M || col0 >= N) return;                       // warp-uniform
+// Fused epilogue of 32 consecutive output columns of ONE row (thread = accumulator row, as tcgen05.ld delivers them):
+// 8 x 16-byte accesses per thread.  (A variant that transposed each 32 x 32 chunk through shared memory so that every warp
+// access was one full 128-byte row segment was measured 2-3x SLOWER on the epilogue-bound shapes -- 32 scalar stores per
+// lane instead of 8 vector stores: the LSU instruction count, not the sector count, is what limits this epilogue.)
+__device__ __forceinline__ void fc_epilogue_store(float (&v)[32], float* __restrict__ C, int ldc, int row, int col, int M, int N,
+                                                  const FcEpi& ep) {
+  if (row >= M || col >= N) return;
   const int flags = ep.flags;
-  uint32_t keep = 0xFFFFFFFFu;
-  if ((flags & kDropout) && row0 + lane < M) {
-    // element (row, col): 16 random bits of Philox(seed, counter = (row * N + col) / 8), slot (row * N + col) % 8
-    const unsigned long long e0 = (unsigned long long)(row0 + lane) * (unsigned long long)N + (unsigned long long)col0;
-    keep = 0u;
+  const bool full = (col + 32 <= N) && ((ldc & 3) == 0);
+  float* dst = C + (size_t)row * ldc + col;
+  if (flags & kBias) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) if (col + j < N) v[j] += __ldg(ep.bias + col + j);
+  }
+  if (flags & kAccum) {
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 p = reinterpret_cast<const float4*>(dst)[j];
+        v[4 * j] += p.x; v[4 * j + 1] += p.y; v[4 * j + 2] += p.z; v[4 * j + 3] += p.w;
+      }
+    } else {
+      for (int j = 0; j < 32 && col + j < N; ++j) v[j] += dst[j];
+    }
+  }
+  if (flags & kRelu) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+  if (flags & kDropout) {
+    // element (row, col + j): 16 random bits of Philox(seed, counter = (row * N + col + j) / 8), slot (.. % 8)
+    const unsigned long long e0 = (unsigned long long)row * (unsigned long long)N + (unsigned long long)col;
     if ((e0 & 7ull) == 0) {
 #pragma unroll
       for (int c4 = 0; c4 < 4; ++c4) {
@@ -140,45 +157,49 @@ __device__ __forceinline__ void fc_epilogue_store(float (&v)[32], float* __restr
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
           const uint32_t bits = (r[t >> 1] >> ((t & 1) * 16)) & 0xFFFFu;
-          keep |= (bits >= ep.drop_thr16 ? 1u : 0u) << (c4 * 8 + t);
+          v[c4 * 8 + t] = bits >= ep.drop_thr16 ? v[c4 * 8 + t] * ep.drop_scale : 0.f;
         }
       }
-    } else {                                                // N % 8 != 0: per-element counters (never on the fc6 / fc7 shapes)
+    } else {                                   // N % 8 != 0: per-element counters (never on the fc6 / fc7 shapes)
       for (int j = 0; j < 32; ++j) {
         uint32_t r[4];
         const unsigned long long e = e0 + j;
         philox4x32_10(ep.seed, e >> 3, r);
         const int t = (int)(e & 7ull);
         const uint32_t bits = (r[t >> 1] >> ((t & 1) * 16)) & 0xFFFFu;
-        keep |= (bits >= ep.drop_thr16 ? 1u : 0u) << j;
+        v[j] = bits >= ep.drop_thr16 ? v[j] * ep.drop_scale : 0.f;
       }
     }
   }
+  if (flags & kMask) {
+    const float* ms = ep.mask_src + (size_t)row * ep.ld_mask + col;
+    if (full && (ep.ld_mask & 3) == 0) {
 #pragma unroll
-  for (int j = 0; j < 32; ++j) sbuf[lane * 33 + j] = v[j];
-  __syncwarp();
-  const int col = col0 + lane;
-  const bool colok = col < N;
-  const float bias = ((flags & kBias) && colok) ? __ldg(ep.bias + col) : 0.f;
-  const int nrows = min(32, M - row0);
-#pragma unroll 4
-  for (int rr = 0; rr < nrows; ++rr) {
-    float x = sbuf[rr * 33 + lane] + bias;
-    const uint32_t kb = (flags & kDropout) ? __shfl_sync(0xFFFFFFFFu, keep, rr) : 0xFFFFFFFFu;
-    if (colok) {
-      float* dst = C + (size_t)(row0 + rr) * ldc + col;
-      if (flags & kAccum) x += *dst;
-      if (flags & kRelu) x = fmaxf(x, 0.f);
-      if (flags & kDropout) x = ((kb >> lane) & 1u) ? x * ep.drop_scale : 0.f;
-      if (flags & kMask) x = __ldg(ep.mask_src + (size_t)(row0 + rr) * ep.ld_mask + col) > 0.f ? x * ep.mask_scale : 0.f;
-      if (flags & kRound) x = rna_tf32(x);
-      *dst = x;
+      for (int j = 0; j < 8; ++j) {
+        const float4 mm = __ldg(reinterpret_cast<const float4*>(ms) + j);
+        v[4 * j] = mm.x > 0.f ? v[4 * j] * ep.mask_scale : 0.f;
+        v[4 * j + 1] = mm.y > 0.f ? v[4 * j + 1] * ep.mask_scale : 0.f;
+        v[4 * j + 2] = mm.z > 0.f ? v[4 * j + 2] * ep.mask_scale : 0.f;
+        v[4 * j + 3] = mm.w > 0.f ? v[4 * j + 3] * ep.mask_scale : 0.f;
+      }
+    } else {
+      for (int j = 0; j < 32 && col + j < N; ++j) v[j] = __ldg(ms + j) > 0.f ? v[j] * ep.mask_scale : 0.f;
     }
   }
-  __syncwarp();                                             // the next chunk reuses sbuf
+  if (flags & kRound) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = rna_tf32(v[j]);
+  }
+  if (full) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  } else {
+    for (int j = 0; j < 32 && col + j < N; ++j) dst[j] = v[j];
+  }
 }
 
-template <bool AMN, bool BMN>
+template <bool AMN, bool BMN, int kStages>
 __global__ void __launch_bounds__(192, 1)
 fc_gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                          const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_b1,
@@ -189,7 +210,6 @@ fc_gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float epi_buf[4][32 * 33];                        // per epilogue warp: transposition buffer of one chunk
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = tc::cluster_ctarank();
@@ -285,7 +305,7 @@ fc_gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
       const int buf = item & 1;
       int m0, n0;
       fc_tile_coords(sk, wi.tile, m0, n0);
-      const int row0 = m0 + (int)crank * kBM + q * 32;          // first row of this warp's 32 accumulator rows
+      const int row = m0 + (int)crank * kBM + trow;
       tc::mbar_wait(&tmem_full_bar[buf], (item >> 1) & 1);
       tc::tc_fence_after();
       if (wi.left_idx < 0) {
@@ -293,7 +313,7 @@ fc_gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         for (int c = 0; c < kBN / 32; ++c) {
           tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * kBN + c * 32, v);
           tc::tmem_ld_wait();
-          fc_epilogue_store(v, epi_buf[q], C, ldc, row0, n0 + c * 32, M, N, ep, lane);
+          fc_epilogue_store(v, C, ldc, row, n0 + c * 32, M, N, ep);
         }
         tc::tc_fence_before();
         tc::mbar_arrive_leader(&tmem_empty_bar[buf]);
@@ -319,7 +339,7 @@ fc_gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     if (fc_item(sk, pair, 0, wi) && wi.left_idx >= 0) {
       int m0, n0;
       fc_tile_coords(sk, wi.tile, m0, n0);
-      const int row0 = m0 + (int)crank * kBM + q * 32;
+      const int row = m0 + (int)crank * kBM + trow;
       const int* counter = sk.flags + wi.left_idx * 2 + crank;
       while (*reinterpret_cast<const volatile int*>(counter) < sk.slices) __nanosleep(64);
       __threadfence();
@@ -335,7 +355,7 @@ fc_gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             v[4 * j] += p.x; v[4 * j + 1] += p.y; v[4 * j + 2] += p.z; v[4 * j + 3] += p.w;
           }
         }
-        fc_epilogue_store(v, epi_buf[q], C, ldc, row0, n0 + ch * 32, M, N, ep, lane);
+        fc_epilogue_store(v, C, ldc, row, n0 + ch * 32, M, N, ep);
       }
     }
   }
@@ -369,9 +389,9 @@ int make_operand_map(CUtensorMap* map, const float* p, int rows, int K, int ld, 
 
 struct FcOperands { const float* A; int lda; const float* B; int ldb; int K; };
 
-template <bool AMN, bool BMN>
-int launch_fc(const FcOperands& o0, const FcOperands& o1, float* C, int ldc, int M, int N, const FcEpi& ep,
-              int max_pairs_cap, cudaStream_t st) {
+template <bool AMN, bool BMN, int kStages>
+int launch_fc_s(const FcOperands& o0, const FcOperands& o1, float* C, int ldc, int M, int N, const FcEpi& ep,
+                int max_pairs_cap, cudaStream_t st) {
   CUtensorMap ma, mb, ma1, mb1;
   int rc = make_operand_map(&ma, o0.A, M, o0.K, o0.lda, AMN);
   if (rc) return rc;
@@ -385,7 +405,7 @@ int launch_fc(const FcOperands& o0, const FcOperands& o1, float* C, int ldc, int
     if (rc) return rc;
   }
   constexpr int smem = kStages * (kBM + kBN / 2) * tc::kTileKBytes + 1024;
-  auto kern = fc_gemm_tf32_2cta_kernel<AMN, BMN>;
+  auto kern = fc_gemm_tf32_2cta_kernel<AMN, BMN, kStages>;
   ODW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(192);
@@ -411,7 +431,8 @@ int launch_fc(const FcOperands& o0, const FcOperands& o1, float* C, int ldc, int
   sk.n_ptiles = sk.m_tiles * sk.n_tiles;
   sk.kiters0 = odw_cdiv(o0.K, tc::kTileK);
   sk.kiters = sk.kiters0 + (o1.K > 0 ? odw_cdiv(o1.K, tc::kTileK) : 0);
-  sk.panel = min(sk.n_tiles, 8);
+  static const int panel_env = fc_env("ODWSCL_FC_PANEL", 8);
+  sk.panel = min(sk.n_tiles, max(panel_env, 1));
   int cap = min(max_pairs, ODW_NUM_SMS / 2);
   if (max_pairs_cap > 0) cap = min(cap, max_pairs_cap);
   if (sk.n_ptiles * 2 <= cap) {
@@ -444,6 +465,15 @@ int launch_fc(const FcOperands& o0, const FcOperands& o1, float* C, int ldc, int
   cfg.gridDim = dim3(2 * sk.np);
   ODW_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, ma1, mb1, C, M, N, ldc, ep, sk));
   return 0;
+}
+
+// ODWSCL_FC_STAGES = 6 | 7 (shared-memory ring depth, 32 KB per stage per CTA), ODWSCL_FC_PANEL = raster panel width
+template <bool AMN, bool BMN>
+int launch_fc(const FcOperands& o0, const FcOperands& o1, float* C, int ldc, int M, int N, const FcEpi& ep,
+              int max_pairs_cap, cudaStream_t st) {
+  static const int stages = fc_env("ODWSCL_FC_STAGES", 6);
+  if (stages >= 7) return launch_fc_s<AMN, BMN, 7>(o0, o1, C, ldc, M, N, ep, max_pairs_cap, st);
+  return launch_fc_s<AMN, BMN, 6>(o0, o1, C, ldc, M, N, ep, max_pairs_cap, st);
 }
 
 // out[c] (+)= sum_r x[r, c]  (bias gradients: db = sum over the batch rows of dZ)

@@ -10,12 +10,14 @@ from odwscl_b200 import capi
 
 R = int(sys.argv[1]) if len(sys.argv) > 1 else 4000
 KC = int(sys.argv[2]) if len(sys.argv) > 2 else 384
+ONLY = set(sys.argv[3].split(",")) if len(sys.argv) > 3 else None
+ITERS = int(os.environ.get("FC_ITERS", "5"))
 torch.backends.cuda.matmul.allow_tf32 = True
 dev = torch.device("cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 
-def timeit(fn, iters=5):
+def timeit(fn, iters=ITERS):
     fn(); fn()
     tot = 0.0
     for _ in range(iters):
@@ -57,6 +59,8 @@ for name, M, N, K, a, b in [
     ("sim2s.wgrad", 128, 4096, 2 * KC, 1, 1), ("sim0s.wgrad", 4096, 4096, 2 * KC, 1, 1), ("fc7s.wgrad", 4096, 4096, 2 * KC, 1, 1),
     ("fc6s.wgrad", 4096, 25088, 2 * KC, 1, 1),
 ]:
+    if ONLY is not None and name not in ONLY:
+        continue
     o, r = case(name, M, N, K, bool(a), bool(b))
     tot_o += o; tot_r += r
 print(json.dumps({"total_ms_ours": round(tot_o, 3), "total_ms_cublas": round(tot_r, 3)}))

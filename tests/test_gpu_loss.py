@@ -181,8 +181,9 @@ def test_model_cfg1_golden(golden):
     model = build_detection_model(cfg)
     model.load_state_dict(orc.synth_state_dict(21, seed=0), strict=True)
     model.cuda().train()
-    model.backbone.body.strict_fp32 = True        # 3-pass TF32 split: fp32-accurate convolutions for the 1e-4 gate
     for m in model.modules():
+        if hasattr(m, "strict_fp32"):
+            m.strict_fp32 = True                  # 3-pass TF32 split: fp32-accurate convolutions / fc GEMMs for the 1e-4 gate
         if isinstance(m, torch.nn.Dropout):
             m.p = 0.0
     images, boxes, labels = orc.synth_batch(1, 256, 600, 600, 21, seed=1234)
