@@ -176,6 +176,16 @@ int odwscl_relu_dropout_bwd_f32(const float* y, const float* gy, float* gx, long
 int odwscl_conv_weight_xform_f32(const float* w_oihw, int Cout, int Cin, float* w_krsc, float* w_crsk_flip,
                                  int round_tf32, odwscl_stream_t stream);
 
+/* ---- A3 + A15 fused (N1): ROIPool forward that ALSO writes the DropBlock-augmented copy of the pooled features
+ * (weak_head.py:107 + :111: out_aug = out * aug_mask[r, bin], aug_mask = block_mask * numel/sum from
+ * odwscl_dropblock_prepare_f32) from the same staged values -- the separate DropBlock pass re-read what this kernel wrote. */
+int odwscl_roi_pool_fwd_nhwc_aug_f32(const float* feat_nhwc, int B, int C, int H, int W, const float* rois, int R,
+                                     float scale, float* out, int32_t* argmax, const float* aug_mask, float* out_aug,
+                                     odwscl_stream_t stream);
+/* scale_io [2] = (sum(block_mask), numel/sum) and mask_out [R, ph*pw] = block_mask * scale from the centre mask alone. */
+int odwscl_dropblock_prepare_f32(const float* centres, int R, int ph, int pw, int block, float* scale_io,
+                                 float* mask_out, odwscl_stream_t stream);
+
 /* ---- A6 / A7 / N1: the fully-connected block -- fc6 + fc7 (modeling/backbone/vgg16.py:122-130,148-162), Sim_Net
  * (roi_heads/sim_head/sim_net.py:10-26) and the MIST predictor heads (roi_heads/weak_head/roi_weak_predictors.py:
  * 158-165); replaces the cuBLAS GEMMs behind nn.Linear forward / backward plus the separate ReLU, Dropout and

@@ -21,7 +21,8 @@ launch_count = 0          # kernels-launching C-ABI calls made so far (bench.py 
 # kernels enqueued per entry point (for the `gpu_launches` bench key)
 _LAUNCHES = {
     "odwscl_roi_pool_fwd_f32": 2, "odwscl_roi_pool_bwd_f32": 1, "odwscl_roi_pool_fwd_nhwc_f32": 1,
-    "odwscl_roi_pool_bwd_nhwc_f32": 1, "odwscl_roi_pool_bwd_nhwc_multi_f32": 1, "odwscl_roi_align_fwd_f32": 1,
+    "odwscl_roi_pool_bwd_nhwc_f32": 1, "odwscl_roi_pool_bwd_nhwc_multi_f32": 1, "odwscl_roi_pool_fwd_nhwc_aug_f32": 1,
+    "odwscl_dropblock_prepare_f32": 3, "odwscl_roi_align_fwd_f32": 1,
     "odwscl_roi_align_bwd_f32": 1, "odwscl_box_iou_f32": 1, "odwscl_nms_f32": 1, "odwscl_nms_legacy_f32": 1,
     "odwscl_discover_phase_a_f32": 2, "odwscl_discover_phase_b_f32": 2, "odwscl_bank_assemble": 1,
     "odwscl_supcon_fwd_f32": 2, "odwscl_supcon_bwd_f32": 1, "odwscl_od_layer_f32": 1,
@@ -40,6 +41,8 @@ _SIGS = {
     "odwscl_roi_pool_bwd_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "odwscl_roi_pool_fwd_nhwc_f32": (_I, [_P, _I, _I, _I, _I, _P, _I, _F, _P, _P, _P]),
     "odwscl_roi_pool_bwd_nhwc_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "odwscl_roi_pool_fwd_nhwc_aug_f32": (_I, [_P, _I, _I, _I, _I, _P, _I, _F, _P, _P, _P, _P, _P]),
+    "odwscl_dropblock_prepare_f32": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
     "odwscl_roi_pool_bwd_nhwc_multi_f32": (_I, [_P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "odwscl_dropblock_mask_f32": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
     "odwscl_roi_align_fwd_f32": (_I, [_P, _I, _I, _I, _I, _P, _I, _F, _I, _I, _I, _P, _P]),
@@ -119,6 +122,9 @@ _WORK = {
     # (feat, B, C, H, W, rois, R, ...): map once + rois + out + int32 argmax
     "odwscl_roi_pool_fwd_nhwc_f32": lambda a: ("byte", 4.0 * a[1] * a[2] * a[3] * a[4] + 20.0 * a[6] + 8.0 * a[6] * a[2] * 49),
     "odwscl_roi_pool_fwd_f32": lambda a: ("byte", 4.0 * a[1] * a[2] * a[3] * a[4] + 20.0 * a[6] + 8.0 * a[6] * a[2] * a[8] * a[9]),
+    # same contract figure for the variant that also writes the augmented copy (its extra 4*R*C*49 bytes replace a
+    # separate pass and are not counted as algorithmic work of ROIPool)
+    "odwscl_roi_pool_fwd_nhwc_aug_f32": lambda a: ("byte", 4.0 * a[1] * a[2] * a[3] * a[4] + 20.0 * a[6] + 8.0 * a[6] * a[2] * 49),
     # (grad, argmax, rois, R, B, C, H, W, ...): grad_out + argmax reads, zero + write of the map
     "odwscl_roi_pool_bwd_nhwc_f32": lambda a: ("byte", 8.0 * a[3] * a[5] * 49 + 8.0 * a[4] * a[5] * a[6] * a[7]),
     "odwscl_roi_pool_bwd_f32": lambda a: ("byte", 8.0 * a[3] * a[5] * a[8] * a[9] + 8.0 * a[4] * a[5] * a[6] * a[7]),
@@ -199,6 +205,27 @@ def roi_pool_forward(feat, rois, scale, ph, pw, out=None):
             _call("odwscl_roi_pool_fwd_f32", _ptr(feat), B, C, H, W, _ptr(rois), R, float(scale), ph, pw,
                   _ptr(out), _ptr(arg), _ptr(ws), ws.numel(), _stream())
     return out, arg
+
+
+def roi_pool_forward_aug(feat, rois, scale, centres, block, buf):
+    """ROIPool (7x7) of a channels-last map into buf[:R] AND its DropBlock-augmented copy into buf[R:] in one pass.
+    Returns (argmax, scale_io, bmask [R,49])."""
+    rois = _chk(rois, torch.float32, "rois")
+    centres = _chk(centres, torch.float32, "centres")
+    B, C, H, W = feat.shape
+    R = rois.shape[0]
+    assert _is_nhwc(feat) and C % 4 == 0 and feat.dtype == torch.float32 and feat.is_cuda
+    assert buf.shape == (2 * R, C, 7, 7) and buf.is_contiguous() and buf.dtype == torch.float32
+    arg = torch.empty((R, C, 7, 7), dtype=torch.int32, device=feat.device)
+    scale_io = torch.empty((2,), dtype=torch.float32, device=feat.device)
+    bmask = torch.empty((R, 49), dtype=torch.float32, device=feat.device)
+    if R == 0:
+        return arg, scale_io, bmask
+    with torch.cuda.device(feat.device):
+        _call("odwscl_dropblock_prepare_f32", _ptr(centres), R, 7, 7, int(block), _ptr(scale_io), _ptr(bmask), _stream())
+        _call("odwscl_roi_pool_fwd_nhwc_aug_f32", _ptr(feat), B, C, H, W, _ptr(rois), R, float(scale), _ptr(buf[:R]),
+              _ptr(arg), _ptr(bmask), _ptr(buf[R:]), _stream())
+    return arg, scale_io, bmask
 
 
 def roi_pool_backward(grad, rois, argmax, ph, pw, B, C, H, W, channels_last=False):

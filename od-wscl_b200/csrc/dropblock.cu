@@ -210,3 +210,24 @@ ODW_API int odwscl_dropblock_seg_f32(const float* x, const float* centres, int R
   ODW_LAUNCH_CHECK();
   return 0;
 }
+
+// scale_io and the per-(roi, bin) factor block_mask * numel/sum from the centre mask alone (both are independent of the
+// values DropBlock multiplies): lets the ROIPool forward write the augmented copy in its own epilogue.
+ODW_API int odwscl_dropblock_prepare_f32(const float* centres, int R, int ph, int pw, int block, float* scale_io,
+                                         float* mask_out, odwscl_stream_t stream) {
+  if (R < 0 || ph <= 0 || pw <= 0 || block <= 0) return ODWSCL_EINVAL;
+  if (R == 0) return 0;
+  if (!centres || !scale_io || !mask_out) return ODWSCL_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  ODW_CUDA(cudaMemsetAsync(scale_io, 0, 2 * sizeof(float), st));
+  const long long total = (long long)R * ph * pw;
+  dropblock_sum_kernel<<<(int)min((long long)ODW_NUM_SMS, (total + 255) / 256), 256, 0, st>>>(centres, R, ph, pw, block,
+                                                                                           scale_io, nullptr);
+  ODW_LAUNCH_CHECK();
+  dropblock_scale_kernel<<<1, 1, 0, st>>>(R, ph, pw, scale_io, nullptr);
+  ODW_LAUNCH_CHECK();
+  dropblock_mask_kernel<<<(int)min((long long)ODW_NUM_SMS * 4, (total + 255) / 256), 256, 0, st>>>(centres, R, ph, pw, block,
+                                                                                                  scale_io, mask_out);
+  ODW_LAUNCH_CHECK();
+  return 0;
+}

@@ -79,7 +79,8 @@ template <int CQT>
 __global__ void __launch_bounds__(7 * 32, 4)
 roi_pool_fwd_nhwc7_kernel(const float4* __restrict__ feat4, const float* __restrict__ rois, int C,
                           int H, int W, float scale, float* __restrict__ out,
-                          int32_t* __restrict__ argmax) {
+                          int32_t* __restrict__ argmax, const float* __restrict__ aug_mask,
+                          float* __restrict__ out_aug) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* s_val = reinterpret_cast<float*>(smem_raw);
   int* s_idx = reinterpret_cast<int*>(smem_raw + kSlab * kBins * sizeof(float));
@@ -141,19 +142,35 @@ roi_pool_fwd_nhwc7_kernel(const float4* __restrict__ feat4, const float* __restr
     __stcs(o4 + i, sv4[i]);
     __stcs(a4 + i, si4[i]);
   }
+  // second output: the DropBlock-augmented copy of the pooled features (weak_head.py:111: x * block_mask * scale),
+  // written from the same staged values -- the separate apply pass would re-read the 200 MB this kernel just wrote
+  if (out_aug != nullptr) {
+    const float* mk = aug_mask + (size_t)n * kBins;            // per-(roi, bin) factor, scale included
+    float4* g4 = reinterpret_cast<float4*>(out_aug + obase);
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+      float4 v = sv4[i];
+      const int k = (4 * i) % kBins;
+      v.x *= __ldg(mk + k);
+      v.y *= __ldg(mk + (k + 1 < kBins ? k + 1 : k + 1 - kBins));
+      v.z *= __ldg(mk + (k + 2 < kBins ? k + 2 : k + 2 - kBins));
+      v.w *= __ldg(mk + (k + 3 < kBins ? k + 3 : k + 3 - kBins));
+      __stcs(g4 + i, v);
+    }
+  }
 }
 
 static int launch_fwd_nhwc7(const float* nhwc, const float* rois, int C, int H, int W, int R, float scale,
-                            float* out, int32_t* argmax, cudaStream_t st) {
+                            float* out, int32_t* argmax, cudaStream_t st, const float* aug_mask = nullptr,
+                            float* out_aug = nullptr) {
   const int smem = kSlab * kBins * (int)(sizeof(float) + sizeof(int));
   dim3 grid(R, odw_cdiv(C, kSlab));
   const float4* f4 = reinterpret_cast<const float4*>(nhwc);
   if (C == 512) {
     ODW_CUDA(cudaFuncSetAttribute(roi_pool_fwd_nhwc7_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    roi_pool_fwd_nhwc7_kernel<128><<<grid, 7 * 32, smem, st>>>(f4, rois, C, H, W, scale, out, argmax);
+    roi_pool_fwd_nhwc7_kernel<128><<<grid, 7 * 32, smem, st>>>(f4, rois, C, H, W, scale, out, argmax, aug_mask, out_aug);
   } else {
     ODW_CUDA(cudaFuncSetAttribute(roi_pool_fwd_nhwc7_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    roi_pool_fwd_nhwc7_kernel<0><<<grid, 7 * 32, smem, st>>>(f4, rois, C, H, W, scale, out, argmax);
+    roi_pool_fwd_nhwc7_kernel<0><<<grid, 7 * 32, smem, st>>>(f4, rois, C, H, W, scale, out, argmax, aug_mask, out_aug);
   }
   ODW_LAUNCH_CHECK();
   return 0;
@@ -420,6 +437,15 @@ ODW_API int odwscl_roi_pool_fwd_nhwc_f32(const float* feat_nhwc, int B, int C, i
   if (R == 0 || C == 0) return 0;
   if (!feat_nhwc || !rois || !out || !argmax) return ODWSCL_EINVAL;
   return launch_fwd_nhwc7(feat_nhwc, rois, C, H, W, R, scale, out, argmax, (cudaStream_t)stream);
+}
+
+ODW_API int odwscl_roi_pool_fwd_nhwc_aug_f32(const float* feat_nhwc, int B, int C, int H, int W, const float* rois, int R,
+                                             float scale, float* out, int32_t* argmax, const float* aug_mask,
+                                             float* out_aug, odwscl_stream_t stream) {
+  if (B < 0 || C < 0 || H <= 0 || W <= 0 || R < 0 || (C & 3)) return ODWSCL_EINVAL;
+  if (R == 0 || C == 0) return 0;
+  if (!feat_nhwc || !rois || !out || !argmax || !aug_mask || !out_aug) return ODWSCL_EINVAL;
+  return launch_fwd_nhwc7(feat_nhwc, rois, C, H, W, R, scale, out, argmax, (cudaStream_t)stream, aug_mask, out_aug);
 }
 
 ODW_API int odwscl_roi_pool_bwd_nhwc_f32(const float* grad_out, const int32_t* argmax, const float* rois, int R, int B,

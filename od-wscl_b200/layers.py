@@ -49,8 +49,14 @@ class _PoolAugFn(Function):
         ph, pw = _pair(output_size)
         R, C = roi.shape[0], input.shape[1]
         buf = torch.empty((2 * R, C, ph, pw), dtype=torch.float32, device=input.device)
-        _, argmax = capi.roi_pool_forward(input, roi, spatial_scale, ph, pw, out=buf[:R])
-        _, scale_io = capi.dropblock(buf[:R], centres, block, out=buf[R:])
+        bmask = None
+        if (ph, pw) == (7, 7) and capi._is_nhwc(input) and C % 4 == 0 and spatial_scale > 0:
+            # one pass: the pooling kernel writes the DropBlock-augmented copy from the values it has staged
+            argmax, scale_io, bmask = capi.roi_pool_forward_aug(input, roi, spatial_scale, centres, block, buf)
+        else:
+            _, argmax = capi.roi_pool_forward(input, roi, spatial_scale, ph, pw, out=buf[:R])
+            _, scale_io = capi.dropblock(buf[:R], centres, block, out=buf[R:])
+        ctx.bmask = bmask
         ctx.save_for_backward(roi, argmax, centres, scale_io)
         ctx.block, ctx.stash, ctx.input_shape, ctx.R = block, stash, input.size(), R
         ctx.channels_last = capi._is_nhwc(input)
@@ -68,7 +74,7 @@ class _PoolAugFn(Function):
         gin = None
         if ctx.channels_last and ctx.out_hw == (7, 7):
             # the DropBlock backward of the augmented half (g[R:] * block_mask * scale) happens inside the scatter
-            bmask = capi.dropblock_mask(centres, ctx.block, scale_io)
+            bmask = ctx.bmask if ctx.bmask is not None else capi.dropblock_mask(centres, ctx.block, scale_io)
             gin = capi.roi_pool_backward_multi(g[:R], g[R:], srows, sgrad, rois, argmax, bs, ch, h, w, mask2=bmask)
         if gin is None:                                                          # maps too large for the plane kernel
             g_aug, _ = capi.dropblock(g[R:], centres, ctx.block, scale_io)

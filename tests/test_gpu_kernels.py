@@ -325,3 +325,20 @@ def test_conv_weight_xform(capi):
     assert torch.equal(wd, w.flip(2, 3).permute(1, 2, 3, 0).contiguous())
     wk_r, wd_r = capi.conv_weight_xform(w, want_fwd=True, want_dgrad=True, round_tf32=True)
     assert torch.equal(wk_r, capi.round_tf32_(wk.clone())) and torch.equal(wd_r, capi.round_tf32_(wd.clone()))
+
+
+def test_roi_pool_forward_with_fused_dropblock_copy(capi):
+    """ROIPool forward that also writes the DropBlock-augmented copy (rows [R, 2R) of the [2R,C,7,7] batch buffer) ==
+    the plain forward followed by the separate DropBlock pass, bit for bit; the stored scale / mask match too."""
+    g = torch.Generator().manual_seed(12)
+    B, C, H, W, R = 2, 64, 38, 50, 333
+    feat = torch.randn(B, C, H, W, generator=g).cuda().contiguous(memory_format=torch.channels_last)
+    rois = _rand_rois(g, B, H, W, R).cuda()
+    cen = (torch.rand(R, 7, 7, generator=g) < 0.3 / 9).float().cuda()
+    buf = torch.empty((2 * R, C, 7, 7), device="cuda")
+    arg, sc, bm = capi.roi_pool_forward_aug(feat, rois, 0.125, cen, 3, buf)
+    out, arg0 = capi.roi_pool_forward(feat, rois, 0.125, 7, 7)
+    aug, sc0 = capi.dropblock(out, cen, 3)
+    assert torch.equal(buf[:R], out) and torch.equal(arg, arg0)
+    assert torch.equal(sc, sc0) and torch.equal(bm, capi.dropblock_mask(cen, 3, sc0))
+    assert torch.equal(buf[R:], aug)
