@@ -412,7 +412,7 @@ def run_ours(args):
     # calibration (part of the set-up, like cudnn.benchmark autotuning): the first steps size the speculative batch bound
     # and the split-K workspaces and fill the caching allocator (steps 2-4 take 40-65 ms, then ~15 ms); every shape of a
     # multi-scale config is visited.  Then exactly --warmup untimed steps, then the timed ones.
-    n_calib = max(5, 2 * len(batches))
+    n_calib = max(10, 2 * len(batches))
     for _ in range(n_calib):
         resident_step()
     torch.cuda.synchronize()

@@ -37,6 +37,10 @@ typedef void* odwscl_stream_t;
 
 int odwscl_version(void);
 const char* odwscl_strerror(int code);
+/* SMs the persistent CTA-pair kernels (conv3x3, fc GEMM) leave unoccupied (rounded down to whole pairs; default 0): with
+ * data-parallel training the NCCL gradient all-reduce (tools/train_net.py:50-55) runs beside the backward kernels and
+ * otherwise waits for a persistent kernel to retire before it gets an SM.  Process-wide; not a per-call argument. */
+int odwscl_set_sm_margin(int sms);
 
 /* ---- A3: ROIPool forward.  Replaces _C.roi_pool_forward (csrc/ROIPool.h:11-24 ->
  * csrc/cuda/ROIPool_cuda.cu:16-77,110-153).  feat [B,C,H,W] fp32 NCHW; rois [R,5] =
@@ -274,6 +278,19 @@ int odwscl_dropblock_rows_f32(const float* x, const float* centres, int R, int C
 int odwscl_dropblock_seg_f32(const float* x, const float* centres, int R, int C, int ph, int pw, int block,
                              float* y, const int32_t* seg_off_dev, int P, float* scale_seg, int reuse_scale,
                              odwscl_stream_t stream);
+
+/* ---- A10 for inputs beyond the single-CTA kernels' 8192 boxes (torchvision.ops.nms has no size limit; the UNION
+ * merge of test-time views, engine/bbox_aug.py:11-141, concatenates every view's proposals): stable rank by counting,
+ * 64 x 64 suppression bit masks, one-CTA sweep -- all on the device.  boxes are read as 4 consecutive floats at
+ * boxes + i * box_stride (box_stride % 4 == 0, 16-byte aligned: a class column of a [N, C*4] tensor needs no copy),
+ * scores at scores + i * score_stride; only candidates with score > score_thr take part (-INFINITY: all).
+ * legacy == 0: torchvision semantics (no +1, IoU > thr), kept indices in DESCENDING score order into keep64 or keep32
+ * (exactly one non-null); legacy != 0: `_C.nms` as csrc/cuda/nms.cu (+1, IoU > thr), ascending original indices into keep64.
+ * ws: odwscl_nms_large_ws_bytes(n) bytes of scratch (order + n * ceil(n/64) mask words). */
+size_t odwscl_nms_large_ws_bytes(int n);
+int odwscl_nms_large_f32(const float* boxes, int box_stride, const float* scores, int score_stride, int n,
+                         float score_thr, float thr, int legacy, int64_t* keep64, int32_t* keep32, int32_t* n_keep,
+                         void* ws, size_t ws_bytes, odwscl_stream_t stream);
 
 /* ---- N4 (test time): PostProcessor.filter_results (roi_heads/box_head/inference.py:216-258) -- for every foreground
  * class j in [1,C): candidates with scores[i,j] > score_thr, torchvision-semantics NMS at `thr` on boxes[i, 4j..4j+3],

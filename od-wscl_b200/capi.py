@@ -51,6 +51,8 @@ _SIGS = {
     "odwscl_nms_f32": (_I, [_P, _P, _I, _F, _P, _P, _P]),
     "odwscl_nms_legacy_f32": (_I, [_P, _P, _I, _F, _P, _P, _P]),
     "odwscl_nms_per_class_f32": (_I, [_P, _P, _I, _I, _F, _F, _P, _P, _P]),
+    "odwscl_nms_large_ws_bytes": (_Z, [_I]),
+    "odwscl_nms_large_f32": (_I, [_P, _I, _P, _I, _I, _F, _F, _I, _P, _P, _P, _P, _Z, _P]),
     "odwscl_discover_phase_a_f32": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _I, _F] + [_P] * 7 + [_P]),
     "odwscl_discover_phase_b_f32": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _I] + [_P] * 8 + [_F] + [_P] * 7 + [_P]),
     "odwscl_bank_assemble": (_I, [_P, _P, _I, _I, _I, _I, _I] + [_P] * 8 + [_I] + [_P] * 4 + [_P]),
@@ -78,6 +80,7 @@ _SIGS = {
     "odwscl_head_scores_f32": (_I, [_P, _I, _I, _I, _I, _P, _I] + [_P] * 7 + [_P]),
     "odwscl_head_loss_f32": (_I, [_P, _I, _I, _I, _I, _I, _P, _I] + [_P] * 8 + [_F, _P, _P, _P, _P]),
     "odwscl_head_grad_scale_f32": (_I, [_P, _I, ctypes.c_longlong, _I, _I, _P, _P]),
+    "odwscl_set_sm_margin": (_I, [_I]),
     "odwscl_version": (_I, []),
     "odwscl_strerror": (ctypes.c_char_p, [_I]),
 }
@@ -98,6 +101,13 @@ def lib():
             fn.restype, fn.argtypes = res, args
         _lib = L
     return _lib
+
+
+def set_sm_margin(sms):
+    """SMs the persistent conv / fc kernels leave to concurrent NCCL kernels (0 = none)."""
+    rc = lib().odwscl_set_sm_margin(int(sms))
+    if rc != 0:
+        raise RuntimeError("odwscl_set_sm_margin(%d) failed" % sms)
 
 
 def _stream():
@@ -305,13 +315,29 @@ def box_iou(a, b, plus_one=True):
     return out
 
 
+NMS_SINGLE_CTA_MAX = 8192      # boxes the one-CTA kernels hold in shared memory; larger inputs take the three-launch path
+
+
+def _nms_large(boxes, box_stride, scores, score_stride, n, score_thr, thr, legacy, keep, cnt):
+    """boxes / scores: tensors whose data_ptr() is the first box / score; strides in floats."""
+    dev = boxes.device
+    ws = _workspace(lib().odwscl_nms_large_ws_bytes(n), dev)
+    k64 = _ptr(keep) if keep.dtype == torch.int64 else None
+    k32 = _ptr(keep) if keep.dtype == torch.int32 else None
+    _call("odwscl_nms_large_f32", _ptr(boxes), int(box_stride), _ptr(scores), int(score_stride), n, float(score_thr),
+          float(thr), int(legacy), k64, k32, _ptr(cnt), _ptr(ws), ws.numel(), _stream())
+
+
 def _nms(name, boxes, scores, thr):
     boxes, scores = _chk(boxes, torch.float32, "boxes").view(-1, 4), _chk(scores, torch.float32, "scores").view(-1)
     n = boxes.shape[0]
     keep = torch.empty((n,), dtype=torch.int64, device=boxes.device)
     cnt = torch.zeros((1,), dtype=torch.int32, device=boxes.device)
     with torch.cuda.device(boxes.device):
-        _call(name, _ptr(boxes), _ptr(scores), n, float(thr), _ptr(keep), _ptr(cnt), _stream())
+        if n > NMS_SINGLE_CTA_MAX:
+            _nms_large(boxes, 4, scores, 1, n, float("-inf"), thr, name == "odwscl_nms_legacy_f32", keep, cnt)
+        else:
+            _call(name, _ptr(boxes), _ptr(scores), n, float(thr), _ptr(keep), _ptr(cnt), _stream())
     return keep, cnt
 
 
@@ -336,10 +362,14 @@ def nms_per_class(boxes, scores, score_thr, nms_thr):
     N, C = scores.shape
     assert boxes.shape == (N, C * 4)
     keep = torch.empty((C, max(N, 1)), dtype=torch.int32, device=boxes.device)
-    cnt = torch.empty((C,), dtype=torch.int32, device=boxes.device)
+    cnt = torch.zeros((C,), dtype=torch.int32, device=boxes.device)
     with torch.cuda.device(boxes.device):
-        _call("odwscl_nms_per_class_f32", _ptr(boxes), _ptr(scores), N, C, float(score_thr), float(nms_thr), _ptr(keep),
-              _ptr(cnt), _stream())
+        if N > NMS_SINGLE_CTA_MAX:      # e.g. the UNION of many test-time views: class by class through the large path
+            for j in range(1, C):
+                _nms_large(boxes[:, 4 * j:], 4 * C, scores[:, j:], C, N, score_thr, nms_thr, False, keep[j], cnt[j:j + 1])
+        else:
+            _call("odwscl_nms_per_class_f32", _ptr(boxes), _ptr(scores), N, C, float(score_thr), float(nms_thr), _ptr(keep),
+                  _ptr(cnt), _stream())
     return keep, cnt
 
 

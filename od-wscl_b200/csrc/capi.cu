@@ -10,3 +10,12 @@ ODW_API const char* odwscl_strerror(int code) {
   if (code > 0) return cudaGetErrorString((cudaError_t)code);
   return "odwscl: unknown error";
 }
+
+static int g_sm_margin = 0;
+int odw_sm_margin() { return g_sm_margin; }
+
+ODW_API int odwscl_set_sm_margin(int sms) {
+  if (sms < 0 || sms > ODW_NUM_SMS - 16) return ODWSCL_EINVAL;
+  g_sm_margin = sms & ~1;                       // whole CTA pairs
+  return 0;
+}

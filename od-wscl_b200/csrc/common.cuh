@@ -21,6 +21,9 @@
 static inline int odw_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline size_t odw_align(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 #define ODW_NUM_SMS 148   // B200: 2 dies x 74 SMs
+// SMs the persistent kernels (conv3x3 split-K pairs, fc GEMM pairs) leave free -- set with odwscl_set_sm_margin() when a
+// concurrent NCCL all-reduce must find SMs without waiting for a persistent kernel to end (capi.cu)
+int odw_sm_margin();
 
 __device__ __forceinline__ float odw_warp_sum(float v) {
 #pragma unroll

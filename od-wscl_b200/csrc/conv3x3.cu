@@ -625,7 +625,7 @@ static int launch_conv_2cta_sk(const CUtensorMap& mx, const CUtensorMap& mw, con
   sk.n_ntiles = Cout / BN;
   sk.n_ptiles = (total_tiles / 2) * sk.n_ntiles;
   sk.kiters = (HALO ? 3 : 9) * (Cin / tc::kTileK);
-  sk.np = min(max_pairs, min(ODW_NUM_SMS / 2, sk.n_ptiles));
+  sk.np = min(max_pairs, min((ODW_NUM_SMS - odw_sm_margin()) / 2, sk.n_ptiles));
   if (sk.np < 8) return 0;               // not enough resident pairs: caller uses the one-tile-per-pair kernel
   sk.rounds = sk.n_ptiles / sk.np;
   sk.left = sk.n_ptiles - sk.rounds * sk.np;

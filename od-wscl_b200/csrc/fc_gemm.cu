@@ -433,7 +433,7 @@ int launch_fc_s(const FcOperands& o0, const FcOperands& o1, float* C, int ldc, i
   sk.kiters = sk.kiters0 + (o1.K > 0 ? odw_cdiv(o1.K, tc::kTileK) : 0);
   static const int panel_env = fc_env("ODWSCL_FC_PANEL", 8);
   sk.panel = min(sk.n_tiles, max(panel_env, 1));
-  int cap = min(max_pairs, ODW_NUM_SMS / 2);
+  int cap = min(max_pairs, (ODW_NUM_SMS - odw_sm_margin()) / 2);
   if (max_pairs_cap > 0) cap = min(cap, max_pairs_cap);
   if (sk.n_ptiles * 2 <= cap) {
     // few tiles (Sim_Net's 128-wide layer, the predictor heads): every tile is split along K over cap / tiles pairs
@@ -452,8 +452,10 @@ int launch_fc_s(const FcOperands& o0, const FcOperands& o1, float* C, int ldc, i
       sk.slices = 0;
     }
   }
-  const size_t ws_floats = (size_t)max(sk.left * sk.slices, 1) * 2 * kBM * kBN;
-  const size_t need = ws_floats * sizeof(float) + (size_t)(sk.left + 1) * 2 * sizeof(int);
+  // sized once for the worst case (left * slices <= resident pairs): no cudaMalloc / cudaFree -- both synchronise the
+  // device -- when a later call has a different shape
+  const size_t ws_floats = (size_t)(ODW_NUM_SMS / 2) * 2 * kBM * kBN;
+  const size_t need = ws_floats * sizeof(float) + (size_t)(ODW_NUM_SMS / 2 + 1) * 2 * sizeof(int);
   if (g_fc_ws_bytes < need) {
     if (g_fc_ws) cudaFree(g_fc_ws);
     ODW_CUDA(cudaMalloc(&g_fc_ws, need));

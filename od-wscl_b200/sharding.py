@@ -39,6 +39,9 @@ def wrap_ddp(model, device=None):
     """DDP exactly as the reference wraps it (tools/train_net.py:50-55: broadcast_buffers=False), with
     static_graph instead of find_unused_parameters -- every parameter receives a gradient on this path."""
     ids = [device.index] if device is not None and device.type == "cuda" else None
+    if ids is not None:
+        from . import capi
+        capi.set_sm_margin(int(os.environ.get("ODWSCL_SM_MARGIN", "0")))      # SMs left to the NCCL all-reduce kernels
     # 611 MB of fp32 gradients per step: large buckets (NVSwitch collectives are latency-, not link-bound) and gradients
     # stored as views of the buckets (no 611 MB grad -> bucket copy before each all-reduce)
     return torch.nn.parallel.DistributedDataParallel(model, device_ids=ids, broadcast_buffers=False,

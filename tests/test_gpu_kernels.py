@@ -162,7 +162,8 @@ def test_iou_nms_golden(capi, golden):
         assert np.array_equal(capi.nms_legacy(P, Su, thr).cpu().numpy(), orc.nms_legacy(G["P"], G["scores_u"], thr, ge=False))
 
 
-@pytest.mark.parametrize("n,ties", [(1, False), (31, True), (700, True), (2000, False), (4000, True)])
+@pytest.mark.parametrize("n,ties", [(1, False), (31, True), (700, True), (2000, False), (4000, True), (8192, True),
+                                    (8193, True), (20000, True)])       # > 8192: the three-launch large path
 def test_nms_random_vs_oracle(capi, n, ties):
     g = torch.Generator().manual_seed(n)
     P = orc.synth_boxes(n, 1000, 600, g)
@@ -176,6 +177,26 @@ def test_nms_random_vs_oracle(capi, n, ties):
         assert np.array_equal(got, orc.nms_tv(P.numpy(), s.numpy(), thr))
     assert np.array_equal(capi.box_iou(P.cuda(), P[:7].cuda(), False).cpu().numpy(),
                           orc.box_iou(P.numpy(), P[:7].numpy(), False))
+
+
+def test_nms_large_legacy_and_per_class(capi):
+    """Beyond the single-CTA limit: `_C.nms` semantics (ascending output) and the all-class test-time filter."""
+    g = torch.Generator().manual_seed(5)
+    n = 9000
+    P = orc.synth_boxes(n, 1000, 600, g)
+    s = (torch.rand(n, generator=g) * 64).round() / 64
+    got = capi.nms_legacy(P.cuda(), s.cuda(), 0.3).cpu().numpy()
+    assert np.array_equal(got, orc.nms_legacy(P.numpy(), s.numpy(), 0.3, False))
+    C = 3
+    boxes = torch.cat([P, P + 3.0, P.flip(0)], dim=1).contiguous()                  # [n, C*4]
+    scores = torch.stack([torch.rand(n, generator=g), s, (torch.rand(n, generator=g) * 8).round() / 8], dim=1).contiguous()
+    keep, cnt = capi.nms_per_class(boxes.cuda(), scores.cuda(), 0.25, 0.4)
+    keep, cnt = keep.cpu().numpy(), cnt.cpu().numpy()
+    assert cnt[0] == 0
+    for j in range(1, C):
+        cand = np.nonzero(scores[:, j].numpy() > np.float32(0.25))[0]
+        exp = cand[orc.nms_tv(boxes[:, 4 * j:4 * j + 4].numpy()[cand], scores[:, j].numpy()[cand], 0.4)]
+        assert np.array_equal(keep[j, :cnt[j]], exp), j
 
 
 def test_nms_empty(capi):

@@ -296,8 +296,11 @@ def test_speculative_k_matches_synced():
     assert float(ev.overflow) == 0.0
     for k in ref_l:
         assert abs(got_l[k] - ref_l[k]) <= 1e-5 * max(abs(ref_l[k]), 1e-3), (k, got_l[k], ref_l[k])
-    for k in ref_g:      # scatter-add / split-K reductions use fp32 atomics: run-to-run order noise, scaled by the tensor
-        torch.testing.assert_close(got_g[k], ref_g[k], rtol=2e-4, atol=2e-4 * float(ref_g[k].abs().max()) + 1e-9)
+    # the padded batch changes the row count of the fc weight-gradient contractions, hence their split-K partition and
+    # summation order (the tensor core adds into TMEM with truncation); scatter-adds use fp32 atomics: order noise,
+    # scaled by the tensor
+    for k in ref_g:
+        torch.testing.assert_close(got_g[k], ref_g[k], rtol=2e-4, atol=1e-3 * float(ref_g[k].abs().max()) + 1e-9)
     ev._k_cap = 1                                  # bound too small: flagged, finite, nothing out of range
     ev._k_event = None
     bad_l, _ = run()

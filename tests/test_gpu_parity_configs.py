@@ -93,8 +93,8 @@ def _run_product(name, mode):
              model.roi_heads.predictor.register_forward_hook(_keep_first("heads"))]
     orig = fe.forward_clean_and_aug
 
-    def wrapped(x, proposals):
-        clean, aug, pooled = orig(x, proposals)
+    def wrapped(x, proposals, **kw):
+        clean, aug, pooled = orig(x, proposals, **kw)
         cap["pooled"], cap["clean"], cap["aug"] = pooled.detach(), clean.detach(), aug.detach()
         return clean, aug, pooled
     fe.forward_clean_and_aug = wrapped
