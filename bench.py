@@ -517,7 +517,8 @@ def run_ours(args):
                                 "TF32 issues at half of it: frac_of_tf32_rate = %.3f" % (2 * roofline["frac"]))
         roofline["timing"] = ("CUDA events around each launch on its stream, live inside %d resident steps "
                               "(WGRAD side-stream overlap off for these steps so durations are per kernel)" % prof_steps)
-        for k in ("odwscl_roi_pool_fwd_nhwc_f32", "odwscl_roi_pool_bwd_nhwc_f32", "odwscl_roi_pool_bwd_nhwc_multi_f32",
+        for k in ("odwscl_roi_pool_fwd_nhwc_f32", "odwscl_roi_pool_fwd_nhwc_aug_f32", "odwscl_roi_pool_bwd_nhwc_f32",
+                  "odwscl_roi_pool_bwd_nhwc_multi_f32",
                   "odwscl_conv3x3_wgrad_nhwc_tf32", "odwscl_conv3x3_nhwc_tf32", "odwscl_fc_gemm_tf32"):
             if k != roofline["kernel"] and entry(k):
                 roofline[k.replace("odwscl_", "")] = entry(k)

@@ -10,7 +10,8 @@ import sys
 KERNEL_TO_ENTRY = [
     ("conv3x3_tf32_2cta", "odwscl_conv3x3_nhwc_tf32"), ("conv3x3_tf32_kernel", "odwscl_conv3x3_nhwc_tf32"),
     ("conv3x3_wgrad_tf32", "odwscl_conv3x3_wgrad_nhwc_tf32"),
-    ("roi_pool_fwd_nhwc7_kernel", "odwscl_roi_pool_fwd_nhwc_f32"),
+    ("roi_pool_fwd_nhwc7_kernel", "odwscl_roi_pool_fwd_nhwc_aug_f32"),
+    ("fc_gemm_tf32_2cta", "odwscl_fc_gemm_tf32"),
     ("roi_pool_bwd_plane_kernel", "odwscl_roi_pool_bwd_nhwc_multi_f32"),
 ]
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
