@@ -60,6 +60,7 @@ def wgrad(x_nhwc, dz_nhwc, w_shape, dil, strict):
 
 
 _side_streams = {}
+_frozen_xform = {}         # (data_ptr, version, shape) -> fprop operand of a FROZEN layer (its weights never change)
 
 
 def _side_stream(device):
@@ -96,6 +97,15 @@ class _VGGStackFn(Function):
                 saved["in%d" % i] = a                   # input of trainable layer i (wgrad; mask of layer i-1)
             if strict:
                 wk = ws[i].permute(0, 2, 3, 1).contiguous()
+            elif not needs_w[i] and i < first_train:
+                # frozen layer (FREEZE_CONV_BODY_AT): the operand layout is computed once and kept
+                key = (ws[i].data_ptr(), ws[i]._version, tuple(ws[i].shape))
+                wk = _frozen_xform.get(key)
+                if wk is None:
+                    for k_old in [k for k in _frozen_xform if k[0] == key[0]]:
+                        del _frozen_xform[k_old]
+                    wk, _ = capi.conv_weight_xform(ws[i], want_fwd=True, want_dgrad=False)
+                    _frozen_xform[key] = wk
             else:       # both operand layouts (fprop now, tap-flipped dgrad later) TF32-rounded in one pass over W
                 wk, wd_ops[i] = capi.conv_weight_xform(ws[i], want_fwd=True, want_dgrad=i > first_train)
             a = _conv(a, wk, bs[i], LAYERS[i][1], capi.CONV_RELU if LAYERS[i][2] else 0, strict, feeds_conv=i < n - 1,

@@ -299,8 +299,12 @@ def test_speculative_k_matches_synced():
     # the padded batch changes the row count of the fc weight-gradient contractions, hence their split-K partition and
     # summation order (the tensor core adds into TMEM with truncation); scatter-adds use fp32 atomics: order noise,
     # scaled by the tensor
+    # Sim_Net's parameters only receive the SupCon gradient (|g| ~ 1e-8 here): the padded batch runs the small fc GEMMs
+    # with another split-K partition, the augmented embeddings move by ~1e-4 (single-pass TF32, truncating TMEM
+    # accumulation) and SupCon at T = 0.2 over cosines packed in [0.9, 1] amplifies that to a few % of max|g|
     for k in ref_g:
-        torch.testing.assert_close(got_g[k], ref_g[k], rtol=2e-4, atol=1e-3 * float(ref_g[k].abs().max()) + 1e-9)
+        a = 0.1 if "model_sim" in k else 1e-3
+        torch.testing.assert_close(got_g[k], ref_g[k], rtol=2e-4, atol=a * float(ref_g[k].abs().max()) + 1e-9)
     ev._k_cap = 1                                  # bound too small: flagged, finite, nothing out of range
     ev._k_event = None
     bad_l, _ = run()
