@@ -234,10 +234,12 @@ int odwscl_colsum_f32(const float* x, long long rows, int cols, int ld, float* o
  * proposals(det) (loss.py:234-246), sm1 / sm2 [R,C] = softmax_c(ref1 / ref2) (the supervisors of branches 1, 2:
  * loss.py:283,313), img_score [B,C] = per-image column sums of final_score (loss.py:352); det_max / det_sum [B,C]
  * (softmax statistics, reused by the loss call) and ref_colsum [3,B,C] (per-image sums of the refinement logits:
- * the accuracy metric of loss.py:25-34) are scratch outputs. */
+ * the accuracy metric of loss.py:25-34) are scratch outputs; ws: odwscl_head_scores_ws_bytes(B, C) bytes (partial
+ * column statistics of the two-stage, fixed-order reductions). */
+size_t odwscl_head_scores_ws_bytes(int B, int C);
 int odwscl_head_scores_f32(const float* logits, int ld, int R, int C, int Q, const int32_t* img_off, int B,
                            float* det_max, float* det_sum, float* ref_colsum, float* final_score, float* sm1,
-                           float* sm2, float* img_score, odwscl_stream_t stream);
+                           float* sm2, float* img_score, void* ws, size_t ws_bytes, odwscl_stream_t stream);
 /* odwscl_head_loss_f32 (after od_layer): pseudo_labels [3,R] int64, label_weights [3,R], reg_targets [3,R,4] as
  * written by odwscl_od_layer_f32; img_labels [B,C] multi-hot.  out11 = (loss_img, loss_ref_cls0, loss_ref_reg0,
  * loss_ref_cls1, loss_ref_reg1, loss_ref_cls2, loss_ref_reg2, acc_img, acc_ref0, acc_ref1, acc_ref2), every entry

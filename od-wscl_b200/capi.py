@@ -31,7 +31,7 @@ _LAUNCHES = {
     "odwscl_maxpool2x2_nhwc_bwd_f32": 1, "odwscl_split_tf32": 1,
     "odwscl_relu_dropout_fwd_f32": 1, "odwscl_relu_dropout_bwd_f32": 1, "odwscl_conv_weight_xform_f32": 1,
     "odwscl_fc_gemm_tf32": 1, "odwscl_colsum_f32": 1,
-    "odwscl_head_scores_f32": 3, "odwscl_head_loss_f32": 2, "odwscl_head_grad_scale_f32": 1,
+    "odwscl_head_scores_f32": 5, "odwscl_head_loss_f32": 2, "odwscl_head_grad_scale_f32": 1,
 }
 
 _P, _I, _F, _Z = c_void_p, c_int, c_float, c_size_t
@@ -77,7 +77,8 @@ _SIGS = {
     "odwscl_fc_gemm_tf32": (_I, [_P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P, _I, _F, _F, ctypes.c_ulonglong, _I,
                                  _P, _I, _P, _I, _I, _P]),
     "odwscl_colsum_f32": (_I, [_P, ctypes.c_longlong, _I, _I, _P, _I, _P]),
-    "odwscl_head_scores_f32": (_I, [_P, _I, _I, _I, _I, _P, _I] + [_P] * 7 + [_P]),
+    "odwscl_head_scores_ws_bytes": (_Z, [_I, _I]),
+    "odwscl_head_scores_f32": (_I, [_P, _I, _I, _I, _I, _P, _I] + [_P] * 7 + [_P, _Z, _P]),
     "odwscl_head_loss_f32": (_I, [_P, _I, _I, _I, _I, _I, _P, _I] + [_P] * 8 + [_F, _P, _P, _P, _P]),
     "odwscl_head_grad_scale_f32": (_I, [_P, _I, ctypes.c_longlong, _I, _I, _P, _P]),
     "odwscl_set_sm_margin": (_I, [_I]),
@@ -657,9 +658,10 @@ def head_scores(logits, C, Q, img_off, B):
     hs.final_score, hs.sm1, hs.sm2 = (torch.empty((R, C), **f32) for _ in range(3))
     hs.img_score = torch.empty((B, C), **f32)
     with torch.cuda.device(dev):
+        ws = _workspace(lib().odwscl_head_scores_ws_bytes(B, C), dev)
         _call("odwscl_head_scores_f32", _ptr(logits), int(ld), R, C, Q, _ptr(_chk(img_off, torch.int32, "img_off")), B,
               _ptr(hs.det_max), _ptr(hs.det_sum), _ptr(hs.ref_colsum), _ptr(hs.final_score), _ptr(hs.sm1), _ptr(hs.sm2),
-              _ptr(hs.img_score), _stream())
+              _ptr(hs.img_score), _ptr(ws), ws.numel(), _stream())
     return hs
 
 
