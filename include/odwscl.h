@@ -254,6 +254,19 @@ int odwscl_head_loss_f32(const float* logits, int ld, int R, int C, int Q, int c
 int odwscl_head_grad_scale_f32(float* grad_logits, int ld, long long R, int C, int Q, const float* upstream7,
                                odwscl_stream_t stream);
 
+/* ---- A7: F.normalize(x, dim=1) at the end of Sim_Net (roi_heads/sim_head/sim_net.py:26; eps 1e-12), forward and
+ * backward as one launch each.  z [R, D] with row pitch ldz; y [R, D] dense; inv_norm [R] = 1 / max(||z||, eps). */
+int odwscl_l2norm_fwd_f32(const float* z, int ldz, int R, int D, float eps, float* y, float* inv_norm,
+                          odwscl_stream_t stream);
+int odwscl_l2norm_bwd_f32(const float* y, const float* g, const float* inv_norm, int R, int D, float eps, float* dz,
+                          odwscl_stream_t stream);
+/* Index bookkeeping of the sync-free contrastive branch (the augmented-positives batch padded to a bound Kc on the
+ * device-resident count *k_dev of Phase-A positives, loss.py:299-310): rows [Kc] = proposal row of every batch slot
+ * (0 for padding), sel [sel_n] = for every entry of the [2K] (drop rows, noise rows) layout the discovery kernels
+ * address, its row in the padded [2 Kc] embedding matrix, *overflow = (K > Kc). */
+int odwscl_spec_index(const int32_t* k_dev, const int32_t* rowsA, int Kc, long long sel_n, int64_t* rows, int64_t* sel,
+                      float* overflow, odwscl_stream_t stream);
+
 /* ---- A15: DropBlock2D apply (modeling/dropblock/drop_block.py:29-66) with a device-sampled
  * centre mask [R,ph,pw] (1.0 = drop centre): block mask by block x block dilation, global
  * renormalisation numel/sum, y = x * mask * scale in ONE pass over x [R,C,ph,pw].

@@ -30,7 +30,8 @@ _LAUNCHES = {
     "odwscl_conv3x3_nhwc_tf32": 1, "odwscl_conv3x3_wgrad_nhwc_tf32": 2, "odwscl_conv3x3_c3_f32": 1, "odwscl_maxpool2x2_nhwc_f32": 1,
     "odwscl_maxpool2x2_nhwc_bwd_f32": 1, "odwscl_split_tf32": 1,
     "odwscl_relu_dropout_fwd_f32": 1, "odwscl_relu_dropout_bwd_f32": 1, "odwscl_conv_weight_xform_f32": 1,
-    "odwscl_fc_gemm_tf32": 1, "odwscl_colsum_f32": 1,
+    "odwscl_fc_gemm_tf32": 1, "odwscl_colsum_f32": 1, "odwscl_l2norm_fwd_f32": 1, "odwscl_l2norm_bwd_f32": 1,
+    "odwscl_spec_index": 1,
     "odwscl_head_scores_f32": 5, "odwscl_head_loss_f32": 2, "odwscl_head_grad_scale_f32": 1,
 }
 
@@ -81,6 +82,9 @@ _SIGS = {
     "odwscl_head_scores_f32": (_I, [_P, _I, _I, _I, _I, _P, _I] + [_P] * 7 + [_P, _Z, _P]),
     "odwscl_head_loss_f32": (_I, [_P, _I, _I, _I, _I, _I, _P, _I] + [_P] * 8 + [_F, _P, _P, _P, _P]),
     "odwscl_head_grad_scale_f32": (_I, [_P, _I, ctypes.c_longlong, _I, _I, _P, _P]),
+    "odwscl_l2norm_fwd_f32": (_I, [_P, _I, _I, _I, _F, _P, _P, _P]),
+    "odwscl_l2norm_bwd_f32": (_I, [_P, _P, _P, _I, _I, _F, _P, _P]),
+    "odwscl_spec_index": (_I, [_P, _P, _I, ctypes.c_longlong, _P, _P, _P, _P]),
     "odwscl_set_sm_margin": (_I, [_I]),
     "odwscl_version": (_I, []),
     "odwscl_strerror": (ctypes.c_char_p, [_I]),
@@ -637,6 +641,37 @@ def colsum(x, out=None, accumulate=False):
     with torch.cuda.device(x.device):
         _call("odwscl_colsum_f32", _ptr(x), rows, cols, int(ld), _ptr(out), int(accumulate), _stream())
     return out
+
+
+def l2norm_forward(z, eps=1e-12):
+    z, ld = _rows2d(z, "z")
+    R, D = z.shape
+    y = torch.empty((R, D), dtype=torch.float32, device=z.device)
+    inv = torch.empty((R,), dtype=torch.float32, device=z.device)
+    with torch.cuda.device(z.device):
+        _call("odwscl_l2norm_fwd_f32", _ptr(z), int(ld), R, D, float(eps), _ptr(y), _ptr(inv), _stream())
+    return y, inv
+
+
+def l2norm_backward(y, g, inv, eps=1e-12):
+    y, g = _chk(y, torch.float32, "y"), _chk(g, torch.float32, "g")
+    R, D = y.shape
+    dz = torch.empty_like(y)
+    with torch.cuda.device(y.device):
+        _call("odwscl_l2norm_bwd_f32", _ptr(y), _ptr(g), _ptr(inv), R, D, float(eps), _ptr(dz), _stream())
+    return dz
+
+
+def spec_index(k_dev, rowsA, Kc, sel_n):
+    """-> (rows int64 [Kc], sel int64 [sel_n], overflow fp32 [1]); see odwscl_spec_index."""
+    dev = rowsA.device
+    rows = torch.empty((Kc,), dtype=torch.int64, device=dev)
+    sel = torch.empty((sel_n,), dtype=torch.int64, device=dev)
+    ovf = torch.empty((1,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _call("odwscl_spec_index", _ptr(_chk(k_dev, torch.int32, "k")), _ptr(_chk(rowsA, torch.int32, "rowsA")), int(Kc),
+              int(sel_n), _ptr(rows), _ptr(sel), _ptr(ovf), _stream())
+    return rows, sel, ovf
 
 
 # ---------------------------------------------------------------- MIL + refinement losses (csrc/head_loss.cu)

@@ -129,3 +129,87 @@ ODW_API int odwscl_conv_weight_xform_f32(const float* w_oihw, int Cout, int Cin,
   ODW_LAUNCH_CHECK();
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// l2norm_rows: F.normalize(z, dim=1) of Sim_Net (roi_heads/sim_head/sim_net.py:26; eps = 1e-12) forward and backward
+// as one launch each (torch: norm + clamp + expand + div, and ~14 kernels in the backward).  Warp per row.
+//   y = z / max(||z||, eps);   dz = (g - y (y . g)) / max(||z||, eps)     (||z|| > eps; else dz = g / eps)
+namespace {
+
+__global__ void __launch_bounds__(256)
+l2norm_fwd_kernel(const float* __restrict__ z, int ldz, int R, int D, float eps, float* __restrict__ y,
+                  float* __restrict__ inv_norm) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= R) return;
+  const float* zr = z + (size_t)r * ldz;
+  float ss = 0.f;
+  for (int c = lane; c < D; c += 32) { const float v = zr[c]; ss += v * v; }
+  ss = odw_warp_sum(ss);
+  const float inv = 1.f / fmaxf(sqrtf(ss), eps);
+  for (int c = lane; c < D; c += 32) y[(size_t)r * D + c] = zr[c] * inv;
+  if (lane == 0) inv_norm[r] = inv;
+}
+
+__global__ void __launch_bounds__(256)
+l2norm_bwd_kernel(const float* __restrict__ y, const float* __restrict__ g, const float* __restrict__ inv_norm, int R,
+                  int D, float eps, float* __restrict__ dz) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= R) return;
+  const float* yr = y + (size_t)r * D;
+  const float* gr = g + (size_t)r * D;
+  float dot = 0.f;
+  for (int c = lane; c < D; c += 32) dot += yr[c] * gr[c];
+  dot = odw_warp_sum(dot);
+  const float inv = inv_norm[r];
+  const bool clamped = inv >= 1.f / eps;                   // ||z|| <= eps: y = z / eps is linear in z
+  for (int c = lane; c < D; c += 32) dz[(size_t)r * D + c] = clamped ? gr[c] * inv : (gr[c] - yr[c] * dot) * inv;
+}
+
+// The index glue of the sync-free contrastive branch (modeling/loss.py, speculative K) in ONE launch instead of ~25 eager
+// kernels: rows[k] = rowsA[k] for k < min(K, Kc) else 0 (the padded augmented-positives batch), sel[j] for j < sel_n =
+// the row of the padded [2 Kc, 128] embedding matrix that entry j of the [2 K] layout (drop rows, then noise rows) reads,
+// padding entries spread over rows; overflow = (K > Kc).
+__global__ void __launch_bounds__(256)
+spec_index_kernel(const int32_t* __restrict__ k_dev, const int32_t* __restrict__ rowsA, int Kc, long long sel_n,
+                  int64_t* __restrict__ rows, int64_t* __restrict__ sel, float* __restrict__ overflow) {
+  const long long K = *k_dev, kv = K < Kc ? K : Kc;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i == 0) *overflow = K > Kc ? 1.f : 0.f;
+  if (i < Kc) rows[i] = i < kv ? (long long)rowsA[i] : 0;
+  if (i < sel_n) {
+    const long long pad = i % (2LL * Kc), jj = i - K;
+    sel[i] = i < K ? (i < kv ? i : pad) : ((jj < kv && i < 2 * K) ? jj + Kc : pad);
+  }
+}
+
+}  // namespace
+
+ODW_API int odwscl_l2norm_fwd_f32(const float* z, int ldz, int R, int D, float eps, float* y, float* inv_norm,
+                                  odwscl_stream_t stream) {
+  if (R < 0 || D <= 0 || ldz < D || eps <= 0.f) return ODWSCL_EINVAL;
+  if (R == 0) return 0;
+  if (!z || !y || !inv_norm) return ODWSCL_EINVAL;
+  l2norm_fwd_kernel<<<odw_cdiv(R, 8), 256, 0, (cudaStream_t)stream>>>(z, ldz, R, D, eps, y, inv_norm);
+  ODW_LAUNCH_CHECK();
+  return 0;
+}
+
+ODW_API int odwscl_l2norm_bwd_f32(const float* y, const float* g, const float* inv_norm, int R, int D, float eps, float* dz,
+                                  odwscl_stream_t stream) {
+  if (R < 0 || D <= 0 || eps <= 0.f) return ODWSCL_EINVAL;
+  if (R == 0) return 0;
+  if (!y || !g || !inv_norm || !dz) return ODWSCL_EINVAL;
+  l2norm_bwd_kernel<<<odw_cdiv(R, 8), 256, 0, (cudaStream_t)stream>>>(y, g, inv_norm, R, D, eps, dz);
+  ODW_LAUNCH_CHECK();
+  return 0;
+}
+
+ODW_API int odwscl_spec_index(const int32_t* k_dev, const int32_t* rowsA, int Kc, long long sel_n, int64_t* rows,
+                              int64_t* sel, float* overflow, odwscl_stream_t stream) {
+  if (Kc <= 0 || sel_n < 0) return ODWSCL_EINVAL;
+  if (!k_dev || !rowsA || !rows || !sel || !overflow) return ODWSCL_EINVAL;
+  const long long n = sel_n > Kc ? sel_n : Kc;
+  spec_index_kernel<<<odw_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(k_dev, rowsA, Kc, sel_n, rows, sel, overflow);
+  ODW_LAUNCH_CHECK();
+  return 0;
+}

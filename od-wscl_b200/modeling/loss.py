@@ -223,24 +223,15 @@ class RoIRegLossComputation(object):
         """Same arithmetic over a batch padded to the bound Kc: rows past the device-resident K are masked (DropBlock
         renormalises each (image, class) segment of the first K rows on its own), and the [2K,128] layout the discovery kernels address (drop rows,
         then noise rows, stride K) is rebuilt with a gather -- nothing is read back."""
-        dev = st.offA.device
         Kc = min(self._k_cap, P * Ncap)
         kdev = st.offA[P:P + 1]                                   # int32 [1], device
-        k64 = kdev.long()
-        kv = torch.clamp(k64, max=Kc)                             # rows that really exist in the padded batch
-        ar = torch.arange(Kc, device=dev)
-        rows = torch.where(ar < kv, st.rowsA[:Kc].long(), torch.zeros_like(ar))
+        # K <= P*Ncap always: every address the discovery kernels form in the [2K] layout is covered by `sel`
+        rows, sel, self.overflow = capi.spec_index(kdev, st.rowsA, Kc, 2 * P * Ncap)
         X = _gather(clean_pooled_feats, rows)
         feature_extractor._aug_rows = rows
         aug = torch.cat([feature_extractor.drop_pool(X, seg_off=st.offA), feature_extractor.noise_pool(X)], dim=0)
         Epad = self._embed(aug, feature_extractor, model_sim)     # [2Kc,128]
-        j = torch.arange(2 * P * Ncap, device=dev)                # K <= P*Ncap always: every address the kernels form is in range
-        jj = j - k64
-        pad = j % (2 * Kc)                     # padding entries spread over rows: their (zero) gradients do not pile up on one
-        idx = torch.where(j < k64, torch.where(j < kv, j, pad),
-                          torch.where((jj < kv) & (j < 2 * k64), jj + Kc, pad))
-        E = Epad.index_select(0, idx).contiguous()
-        self.overflow = (k64 > Kc).float()
+        E = Epad.index_select(0, sel).contiguous()
         self._record_k(kdev)
         return E, Kc
 

@@ -11,6 +11,22 @@ from torch.autograd.function import once_differentiable
 from .. import capi
 
 
+class _L2NormFn(Function):
+    """F.normalize(z, dim=1) (sim_net.py:26) as one kernel forward, one backward (csrc/elementwise.cu)."""
+
+    @staticmethod
+    def forward(ctx, z):
+        y, inv = capi.l2norm_forward(z)
+        ctx.save_for_backward(y, inv)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        y, inv = ctx.saved_tensors
+        return capi.l2norm_backward(y, g.contiguous(), inv)
+
+
 class Sim_Net(nn.Module):
     def __init__(self, config, in_dim):
         super().__init__()
@@ -34,9 +50,9 @@ class Sim_Net(nn.Module):
         h = fc.linear(roi_feat, self.mlp[0].weight, self.mlp[0].bias, act=fc.ACT_RELU, round_out=True,
                       strict=self.strict_fp32, in_mask_scale=in_mask_scale, act_bwd_fused=fuse,
                       stash=st["mlp0"] if st is not None else None, role=role if st is not None else None)
-        return F.normalize(fc.linear(h, self.mlp[2].weight, self.mlp[2].bias, strict=self.strict_fp32,
-                                     in_mask_scale=1.0 if fuse else None, stash=st["mlp2"] if st is not None else None,
-                                     role=role if st is not None else None), dim=1)
+        return _L2NormFn.apply(fc.linear(h, self.mlp[2].weight, self.mlp[2].bias, strict=self.strict_fp32,
+                                         in_mask_scale=1.0 if fuse else None, stash=st["mlp2"] if st is not None else None,
+                                         role=role if st is not None else None))
 
 
 class _SupConBankFn(Function):
