@@ -377,10 +377,16 @@ def run_ours(args):
         bt["rois_d"] = bt["rois_h"].to(dev, non_blocking=True)
         bt["props_d"] = props_from(bt["rois_d"], bt)
 
+    debug = os.environ.get("ODWSCL_BENCH_DEBUG", "") not in ("", "0")
+
     def resident_step():
         bt = batches[counter["resident"] % len(batches)]
         counter["resident"] += 1
-        step(bt["images_d"], bt["props_d"], bt["targets"])
+        total = step(bt["images_d"], bt["props_d"], bt["targets"])
+        if debug:                                          # synchronising trace of every step (never on in a measurement)
+            torch.cuda.synchronize()
+            print("[bench-debug] step %d scale %s loss %.6f K-bound %s" % (counter["resident"], bt["wh"], float(total),
+                                                                           evaluator._k_cap), file=sys.stderr, flush=True)
 
     from odwscl_b200.data import HostPrefetcher
     prefetch = HostPrefetcher(dev)

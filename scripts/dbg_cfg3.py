@@ -24,3 +24,14 @@ with torch.no_grad():
     print("cls", fin(cls), "det", fin(det), [fin(r) for r in refs], [fin(b) for b in bbs])
 torch.cuda.synchronize()
 print("ok")
+# ---- full train-mode forward with the loss (the bench's call)
+targets = []
+for lab in labels:
+    t = BoxList(torch.zeros((len(lab), 4)), (W, H), "xyxy"); t.add_field("labels", torch.as_tensor(lab)); targets.append(t)
+print("labels", labels)
+losses, _ = model(images.cuda(), targets, props)
+torch.cuda.synchronize()
+print({k: float(v) for k, v in losses.items()})
+sum(losses.values()).backward()
+torch.cuda.synchronize()
+print("backward ok")
