@@ -47,7 +47,7 @@ __device__ __forceinline__ int cta_argmax_first(float v, int idx, float* s_v, in
     if (lane == 0) s_i[0] = idx;
   }
   __syncthreads();
-  const int r = s_i[0];
+  const int r = s_i[0] == INT_MAX ? 0 : s_i[0];   // all-NaN column (diverged training): stay in range, do not fault
   __syncthreads();
   return r;
 }
