@@ -82,6 +82,9 @@ def parse():
     ap.add_argument("--profile-range", action="store_true",
                     help="bracket the timed resident steps with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     ap.add_argument("--cpu-sample-props", type=int, default=2000)
+    ap.add_argument("--no-allreduce", action="store_true",
+                    help="diagnosis (N > 1): run the DDP step under no_sync() -- the difference to the normal step is the exposed "
+                         "cost of the gradient all-reduce")
     return ap.parse_args()
 
 
@@ -334,11 +337,15 @@ def run_ours(args):
     evaluator.k_margin, evaluator.k_granule = args.k_margin, args.k_granule
     overflow_log = []
 
+    import contextlib
+
     def step(images_d, props, targets):
-        losses, _ = step_model(images_d, targets, props)
-        total = sum(losses.values())
-        opt.zero_grad(set_to_none=True)
-        total.backward()
+        sync_ctx = step_model.no_sync() if (args.no_allreduce and world > 1) else contextlib.nullcontext()
+        with sync_ctx:
+            losses, _ = step_model(images_d, targets, props)
+            total = sum(losses.values())
+            opt.zero_grad(set_to_none=True)
+            total.backward()
         flag = evaluator.overflow
         if flag is not None:
             if world > 1:
@@ -573,6 +580,7 @@ def run_ours(args):
             "config": {"workload": WORKLOAD,
                        "images_per_gpu": B_PER_GPU, "proposals_per_image": N_PROP, "parallelism": "dp%d" % world,
                        "host_syncs_per_step": 1 if args.sync_k else 0, "skipped_updates": [skipped, skipped_e2e],
+                       "allreduce": not args.no_allreduce, "sm_margin": int(os.environ.get("ODWSCL_SM_MARGIN", "0")),
                        "calibration_steps": n_calib, "first_window_with_skipped_update": first_window,
                        "lr": LR, "final_loss": float(loss_h[0]),
                        "l2": "per-step working set (>=1.6 GB of activations) exceeds the 126 MB L2; kernel-alone timings flush L2 with a 256 MB write"},

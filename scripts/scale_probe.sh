@@ -1,0 +1,17 @@
+#!/bin/bash
+# multi-GPU diagnosis: step time with / without the gradient all-reduce, and with SMs left to NCCL.  usage: scale_probe.sh <tag> <N>
+TAG=${1:-scale}; N=${2:-2}
+OUT=gpurun_out/$TAG; mkdir -p $OUT
+run() {  # name, env, extra args
+  env $2 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
+      bench.py --gpus $N --steps 10 --warmup 3 --no-cpu-baseline $3 > $OUT/$1.json 2> $OUT/$1.err
+  echo "$1 rc=$?"; python -c "
+import json,sys
+d=json.load(open('$OUT/$1.json')); print('$1', 'ms/step', round(d['ms_per_step'],2), 'value', round(d['value']), 'e2e ms', round(d['e2e']['ms_per_step'],2))" 2>/dev/null || tail -3 $OUT/$1.err
+}
+run n${N}_default "ODWSCL_SM_MARGIN=0" ""
+run n${N}_nosync "ODWSCL_SM_MARGIN=0" "--no-allreduce"
+run n${N}_margin8 "ODWSCL_SM_MARGIN=8" ""
+run n${N}_maxctas8 "ODWSCL_SM_MARGIN=0 NCCL_MAX_CTAS=8" ""
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $OUT/n1.json 2> $OUT/n1.err; python -c "
+import json; d=json.load(open('$OUT/n1.json')); print('n1 ms/step', round(d['ms_per_step'],2), 'value', round(d['value']))"
