@@ -307,6 +307,17 @@ int odwscl_nms_large_f32(const float* boxes, int box_stride, const float* scores
                          float score_thr, float thr, int legacy, int64_t* keep64, int32_t* keep32, int32_t* n_keep,
                          void* ws, size_t ws_bytes, odwscl_stream_t stream);
 
+/* ---- the augmented positives of the contrastive branch (roi_heads/weak_head/loss.py:296-305) in one pass: for slot k
+ * (proposal rows[k] of pooled [R, D], D = C * cells, cells = 7 * pw) out[k] = DropBlock(block x block) view, renormalised
+ * per segment (seg_off_dev [P+1]; modeling/backbone/vgg16.py:173-175), out[Kc + k] = eps * x + x, eps ~ N(0,1) (vgg16.py:
+ * 177-180; Philox keyed by (seed, k * D + e), or `noise` [Kc, D] when given).  Slots >= seg_off[P] are padding (zeros).
+ * compute_scale != 0 fills scale_seg [P,2] from the centres first.  backward != 0: src = gradient of out [2 Kc, D],
+ * dst [Kc, D] = gradient w.r.t. the gathered pooled rows (same masks, same noise). */
+int odwscl_aug_positives_f32(const float* src, int D, int cells, const int64_t* rows, int Kc, const int32_t* seg_off_dev,
+                             int P, const float* centres, int block, float* scale_seg, int compute_scale,
+                             const float* noise, unsigned long long seed, int backward, float* dst,
+                             odwscl_stream_t stream);
+
 /* ---- N4 (test time): PostProcessor.filter_results (roi_heads/box_head/inference.py:216-258) -- for every foreground
  * class j in [1,C): candidates with scores[i,j] > score_thr, torchvision-semantics NMS at `thr` on boxes[i, 4j..4j+3],
  * all classes in ONE launch (one CTA per class, sort + sweep in shared memory, no host round trip).  boxes [N,C*4],

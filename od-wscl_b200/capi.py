@@ -31,7 +31,7 @@ _LAUNCHES = {
     "odwscl_maxpool2x2_nhwc_bwd_f32": 1, "odwscl_split_tf32": 1,
     "odwscl_relu_dropout_fwd_f32": 1, "odwscl_relu_dropout_bwd_f32": 1, "odwscl_conv_weight_xform_f32": 1,
     "odwscl_fc_gemm_tf32": 1, "odwscl_colsum_f32": 1, "odwscl_l2norm_fwd_f32": 1, "odwscl_l2norm_bwd_f32": 1,
-    "odwscl_spec_index": 1,
+    "odwscl_spec_index": 1, "odwscl_aug_positives_f32": 2,
     "odwscl_head_scores_f32": 5, "odwscl_head_loss_f32": 2, "odwscl_head_grad_scale_f32": 1,
 }
 
@@ -85,6 +85,7 @@ _SIGS = {
     "odwscl_l2norm_fwd_f32": (_I, [_P, _I, _I, _I, _F, _P, _P, _P]),
     "odwscl_l2norm_bwd_f32": (_I, [_P, _P, _P, _I, _I, _F, _P, _P]),
     "odwscl_spec_index": (_I, [_P, _P, _I, ctypes.c_longlong, _P, _P, _P, _P]),
+    "odwscl_aug_positives_f32": (_I, [_P, _I, _I, _P, _I, _P, _I, _P, _I, _P, _I, _P, ctypes.c_ulonglong, _I, _P, _P]),
     "odwscl_set_sm_margin": (_I, [_I]),
     "odwscl_version": (_I, []),
     "odwscl_strerror": (ctypes.c_char_p, [_I]),
@@ -660,6 +661,29 @@ def l2norm_backward(y, g, inv, eps=1e-12):
     with torch.cuda.device(y.device):
         _call("odwscl_l2norm_bwd_f32", _ptr(y), _ptr(g), _ptr(inv), R, D, float(eps), _ptr(dz), _stream())
     return dz
+
+
+def aug_positives(src, rows, seg_off, P, centres, block, scale_seg=None, noise=None, seed=0, backward=False):
+    """Forward: src = pooled [R,C,7,7] (or [R, D]) -> out [2 Kc, C,7,7] (DropBlock views, then noise views), scale_seg [P,2].
+    Backward: src = gradient of out -> gradient w.r.t. the Kc gathered rows."""
+    src = _chk(src, torch.float32, "src")
+    centres = _chk(centres, torch.float32, "centres")
+    Kc, ph, pw = centres.shape
+    cells = ph * pw
+    D = src[0].numel()
+    compute = scale_seg is None
+    if compute:
+        scale_seg = torch.empty((P, 2), dtype=torch.float32, device=src.device)
+    if noise is not None:
+        noise = _chk(noise, torch.float32, "noise")
+        assert noise.numel() == Kc * D
+    dst = torch.empty(((Kc if backward else 2 * Kc),) + tuple(src.shape[1:]), dtype=torch.float32, device=src.device)
+    if Kc > 0:
+        with torch.cuda.device(src.device):
+            _call("odwscl_aug_positives_f32", _ptr(src), D, cells, _ptr(_chk(rows, torch.int64, "rows")), Kc,
+                  _ptr(_chk(seg_off, torch.int32, "seg_off")), int(P), _ptr(centres), int(block), _ptr(scale_seg), int(compute),
+                  _ptr(noise), ctypes.c_ulonglong(seed & (2 ** 64 - 1)), int(backward), _ptr(dst), _stream())
+    return dst, scale_seg
 
 
 def spec_index(k_dev, rowsA, Kc, sel_n):

@@ -231,3 +231,112 @@ ODW_API int odwscl_dropblock_prepare_f32(const float* centres, int R, int ph, in
   ODW_LAUNCH_CHECK();
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// The augmented positives of the contrastive branch (roi_heads/weak_head/loss.py:296-305) in one pass over the pooled
+// rows: for every Phase-A positive k (proposal rows[k]) the DropBlock(1x1, p = 0.3) view x * mask * numel/sum
+// (vgg16.py:173-175, renormalised per (image, class) segment as the reference's per-group calls are) goes to out[k] and
+// the multiplicative-noise view eps * x + x, eps ~ N(0,1) (vgg16.py:177-180) to out[Kc + k].  Replaces a gather, a
+// DropBlock pass, randn, a multiply, an add and a concatenation (6 passes over [Kc, C*49]) and their backward.  The
+// noise is Philox4x32-10 + Box-Muller keyed by (seed, k * D + e) -- regenerated in the backward -- unless a noise tensor
+// is handed in (tests replay the CPU checker's draws); rows >= seg_off[P] are padding (zero).
+namespace {
+
+__device__ __forceinline__ void philox_round_db(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+  const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+// four N(0,1) draws for counter `ctr`
+__device__ __forceinline__ float4 philox_normal4(unsigned long long seed, unsigned long long ctr) {
+  uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), 0x5EED0A06u, 0u};
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round_db(c, k0, k1);
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  const float u0 = ((c[0] >> 8) + 1u) * (1.f / 16777216.f), u1 = (c[1] >> 8) * (1.f / 16777216.f);   // u0 in (0,1]
+  const float u2 = ((c[2] >> 8) + 1u) * (1.f / 16777216.f), u3 = (c[3] >> 8) * (1.f / 16777216.f);
+  const float r0 = sqrtf(-2.f * logf(u0)), r1 = sqrtf(-2.f * logf(u2));
+  float s0, c0, s1, c1;
+  sincospif(2.f * u1, &s0, &c0);
+  sincospif(2.f * u3, &s1, &c1);
+  return make_float4(r0 * c0, r0 * s0, r1 * c1, r1 * s1);
+}
+
+template <bool kBackward>
+__global__ void __launch_bounds__(256)
+aug_positives_kernel(const float* __restrict__ src /* fwd: pooled [R,D]; bwd: g [2Kc,D] */, int D, int cells,
+                     const int64_t* __restrict__ rows, int Kc, const int32_t* __restrict__ seg_off, int P,
+                     const float* __restrict__ centres, int block, const float* __restrict__ scale_seg,
+                     const float* __restrict__ noise, unsigned long long seed, float* __restrict__ dst) {
+  extern __shared__ float s_bm[];
+  const int k = blockIdx.x;
+  const int ph = 7, pw = cells / 7;
+  const bool valid = k < seg_off[P];
+  float* d_drop = dst + (size_t)k * D;                               // fwd: out[k];  bwd: gx[k]
+  float* d_noise = kBackward ? nullptr : dst + (size_t)(Kc + k) * D; // fwd: out[Kc + k]
+  if (!valid) {
+    for (int t = threadIdx.x; t < D / 4; t += blockDim.x) {
+      reinterpret_cast<float4*>(d_drop)[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!kBackward) reinterpret_cast<float4*>(d_noise)[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    return;
+  }
+  int lo = 0, hi = P - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (seg_off[mid] <= k) lo = mid; else hi = mid - 1;
+  }
+  const float scale = scale_seg[2 * lo + 1];
+  for (int b = threadIdx.x; b < cells; b += blockDim.x)
+    s_bm[b] = block_mask_at(centres + (size_t)k * cells, ph, pw, block, b / pw, b % pw) * scale;
+  __syncthreads();
+  const float4* a4 = reinterpret_cast<const float4*>(kBackward ? src + (size_t)k * D : src + (size_t)rows[k] * D);
+  const float4* b4 = kBackward ? reinterpret_cast<const float4*>(src + (size_t)(Kc + k) * D) : nullptr;
+  const float4* n4 = noise ? reinterpret_cast<const float4*>(noise + (size_t)k * D) : nullptr;
+  for (int t = threadIdx.x; t < D / 4; t += blockDim.x) {
+    const float4 x = __ldg(a4 + t);                                  // fwd: pooled row;  bwd: gradient of the drop view
+    const float4 e = n4 ? __ldg(n4 + t) : philox_normal4(seed, ((unsigned long long)k * D + 4ull * t) >> 2);
+    const int q = (4 * t) % cells;
+    const float m0 = s_bm[q], m1 = s_bm[q + 1 < cells ? q + 1 : q + 1 - cells], m2 = s_bm[q + 2 < cells ? q + 2 : q + 2 - cells],
+                m3 = s_bm[q + 3 < cells ? q + 3 : q + 3 - cells];
+    if (!kBackward) {
+      reinterpret_cast<float4*>(d_drop)[t] = make_float4(x.x * m0, x.y * m1, x.z * m2, x.w * m3);
+      reinterpret_cast<float4*>(d_noise)[t] = make_float4(__fadd_rn(__fmul_rn(e.x, x.x), x.x), __fadd_rn(__fmul_rn(e.y, x.y), x.y),
+                                                         __fadd_rn(__fmul_rn(e.z, x.z), x.z), __fadd_rn(__fmul_rn(e.w, x.w), x.w));
+    } else {
+      const float4 g2 = __ldg(b4 + t);                               // gradient of the noise view: d/dx = eps + 1
+      reinterpret_cast<float4*>(d_drop)[t] =
+          make_float4(__fadd_rn(x.x * m0, __fadd_rn(__fmul_rn(g2.x, e.x), g2.x)), __fadd_rn(x.y * m1, __fadd_rn(__fmul_rn(g2.y, e.y), g2.y)),
+                      __fadd_rn(x.z * m2, __fadd_rn(__fmul_rn(g2.z, e.z), g2.z)), __fadd_rn(x.w * m3, __fadd_rn(__fmul_rn(g2.w, e.w), g2.w)));
+    }
+  }
+}
+
+}  // namespace
+
+// forward: compute_scale != 0 first fills scale_seg from the centres (per-segment numel / sum)
+ODW_API int odwscl_aug_positives_f32(const float* src, int D, int cells, const int64_t* rows, int Kc, const int32_t* seg_off_dev,
+                                     int P, const float* centres, int block, float* scale_seg, int compute_scale,
+                                     const float* noise, unsigned long long seed, int backward, float* dst,
+                                     odwscl_stream_t stream) {
+  if (D <= 0 || (D & 3) || cells <= 0 || cells % 7 || D % cells || Kc < 0 || P <= 0 || block <= 0) return ODWSCL_EINVAL;
+  if (Kc == 0) return 0;
+  if (!src || !seg_off_dev || !centres || !scale_seg || !dst || (!backward && !rows)) return ODWSCL_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (compute_scale) {
+    dropblock_seg_sum_kernel<<<P, 256, 0, st>>>(centres, Kc, 7, cells / 7, block, seg_off_dev, scale_seg);
+    ODW_LAUNCH_CHECK();
+  }
+  if (backward)
+    aug_positives_kernel<true><<<Kc, 256, cells * sizeof(float), st>>>(src, D, cells, rows, Kc, seg_off_dev, P, centres, block,
+                                                                       scale_seg, noise, seed, dst);
+  else
+    aug_positives_kernel<false><<<Kc, 256, cells * sizeof(float), st>>>(src, D, cells, rows, Kc, seg_off_dev, P, centres, block,
+                                                                        scale_seg, noise, seed, dst);
+  ODW_LAUNCH_CHECK();
+  return 0;
+}

@@ -108,6 +108,35 @@ class _GatherRowsFn(Function):
         return None, None, None, None
 
 
+class _AugPositivesFn(Function):
+    """The DropBlock and the noise views of the Phase-A positives (loss.py:296-305) straight from the clean half of a
+    _PoolAugFn buffer: one kernel instead of gather + DropBlock + randn + mul + add + cat; the gradient w.r.t. the gathered
+    rows is handed to the ROIPool backward through `stash` (as _GatherRowsFn does)."""
+
+    @staticmethod
+    def forward(ctx, buf, rows, R, stash, seg_off, P, centres, block, noise, seed):
+        out, scale_seg = capi.aug_positives(buf[:R], rows, seg_off, P, centres, block, noise=noise, seed=seed)
+        ctx.save_for_backward(rows, seg_off, centres, scale_seg, noise if noise is not None else rows.new_zeros(0))
+        ctx.stash, ctx.P, ctx.block, ctx.seed, ctx.has_noise = stash, P, block, seed, noise is not None
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        rows, seg_off, centres, scale_seg, noise = ctx.saved_tensors
+        gx, _ = capi.aug_positives(g.contiguous(), rows, seg_off, ctx.P, centres, ctx.block, scale_seg=scale_seg,
+                                   noise=noise if ctx.has_noise else None, seed=ctx.seed, backward=True)
+        if "rows" in ctx.stash:
+            ctx.stash["rows"] = torch.cat([ctx.stash["rows"], rows])
+            ctx.stash["grads"] = torch.cat([ctx.stash["grads"], gx])
+        else:
+            ctx.stash["rows"], ctx.stash["grads"] = rows, gx
+        return (None,) * 10
+
+
+aug_positives = _AugPositivesFn.apply
+
+
 class _SplitRowsFn(Function):
     """x[:R], x[R:] as two outputs whose backward is ONE concatenation (instead of two zero-padded slices + an add)."""
 

@@ -182,6 +182,17 @@ class RoIRegLossComputation(object):
             self._k_event.record()
 
     @staticmethod
+    def _batched_views(clean_pooled_feats, rows, seg_off, P, feature_extractor):
+        """[DropBlock views ; noise views] of the positives `rows`, every (image, class) segment renormalised on its own
+        (loss.py:299): one fused kernel when the pooled tensor comes from forward_clean_and_aug, else op by op."""
+        fused = getattr(clean_pooled_feats, "_odw_aug_positives", None)
+        if fused is not None and rows.numel() > 0:
+            return fused(rows, seg_off, P)
+        X = _gather(clean_pooled_feats, rows)
+        feature_extractor._aug_rows = rows                       # test hook: row-keyed replay of the stochastic layers
+        return torch.cat([feature_extractor.drop_pool(X, seg_off=seg_off), feature_extractor.noise_pool(X)], dim=0)
+
+    @staticmethod
     def _embed(aug, feature_extractor, model_sim):
         """Sim_Net(neck(aug)) (loss.py:300-301,304-305).  Sim_Net is the only consumer of this neck call, so fc7's
         ReLU/Dropout derivative rides in Sim_Net's dgrad epilogue (fc.linear in_mask_scale) when the extractor supports it."""
@@ -203,10 +214,7 @@ class RoIRegLossComputation(object):
             self.overflow = torch.zeros((1,), dtype=torch.float32, device=st.offA.device)
         rows = st.rowsA[:K].long()
         if self.batch_aug:
-            X = _gather(clean_pooled_feats, rows)
-            feature_extractor._aug_rows = rows                   # test hook: row-keyed replay of the stochastic layers
-            # one launch over all (image, class) groups; DropBlock renormalises each group on its own (loss.py:299)
-            aug = torch.cat([feature_extractor.drop_pool(X, seg_off=st.offA), feature_extractor.noise_pool(X)], dim=0)
+            aug = self._batched_views(clean_pooled_feats, rows, st.offA, P, feature_extractor)
         else:
             drops, noises = [], []
             for p in range(P):
@@ -227,9 +235,7 @@ class RoIRegLossComputation(object):
         kdev = st.offA[P:P + 1]                                   # int32 [1], device
         # K <= P*Ncap always: every address the discovery kernels form in the [2K] layout is covered by `sel`
         rows, sel, self.overflow = capi.spec_index(kdev, st.rowsA, Kc, 2 * P * Ncap)
-        X = _gather(clean_pooled_feats, rows)
-        feature_extractor._aug_rows = rows
-        aug = torch.cat([feature_extractor.drop_pool(X, seg_off=st.offA), feature_extractor.noise_pool(X)], dim=0)
+        aug = self._batched_views(clean_pooled_feats, rows, st.offA, P, feature_extractor)
         Epad = self._embed(aug, feature_extractor, model_sim)     # [2Kc,128]
         E = Epad.index_select(0, sel).contiguous()
         self._record_k(kdev)

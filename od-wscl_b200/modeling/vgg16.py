@@ -162,7 +162,27 @@ class VGG16FC67ROIFeatureExtractor(nn.Module):
         clean, aug = split_rows(feats, R)
         pooled = buf.detach()[:R]
         pooled._odw_gather = lambda rows: gather_rows(buf, rows, R, stash)
+        pooled._odw_aug_positives = lambda rows, seg_off, P: self._aug_positives(buf, rows, R, stash, seg_off, P)
         return clean, aug, pooled
+
+    def _aug_positives(self, buf, rows, R, stash, seg_off, P):
+        """[drop_pool(x); noise_pool(x)] of the rows `rows` of the clean pooled features (vgg16.py:173-180) in one kernel;
+        the test hooks (centre_sampler / noise_sampler) are honoured."""
+        from ..layers import aug_positives
+        from . import fc
+        db = self.sim_drop
+        n = rows.numel()
+        gamma = db.drop_prob / (db.block_size ** 2)
+        self._aug_rows = rows
+        if db.centre_sampler is not None:
+            centres = db.centre_sampler(n, 7, 7, gamma, rows.device)
+        else:
+            centres = (torch.rand(n, 7, 7, device=rows.device) < gamma).float()
+        noise = None
+        if self.noise_sampler is not None:
+            noise = self.noise_sampler((n,) + tuple(buf.shape[1:]), rows.device).contiguous()
+        return aug_positives(buf, rows, R, stash, seg_off, P, centres.contiguous(), db.block_size, noise,
+                             fc.next_dropout_seed())
 
     def forward_pooler(self, x, proposals):
         return self.pooler(x, proposals)
