@@ -90,14 +90,32 @@ def parse():
 
 # ------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """SM clock + throttle reasons during the timed regions.  In-process NVML (nvidia_ml_py) polled by a thread every 50 ms;
+    `nvidia-smi -lms 100` as a child process only when NVML cannot be loaded (ODWSCL_CLOCKS=smi forces it, =off disables
+    sampling).  Round 2 found isolated 50-150 ms HOST stalls of the enqueueing thread in 1-3 of 10 steps with the
+    nvidia-smi child running (none in 80 steps without it: scripts/host_stall_probe.py)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.mode = index, [], None, os.environ.get("ODWSCL_CLOCKS", "nvml")
+        self._stop = False
 
     def start(self):
+        if self.mode == "off":
+            return
+        if self.mode != "smi":
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
+                self.t = threading.Thread(target=self._poll_nvml, daemon=True)
+                self.t.start()
+                self.mode = "nvml"
+                return
+            except Exception:
+                self.mode = "smi"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -106,6 +124,31 @@ class ClockSampler:
             self.t.start()
         except Exception:
             self.proc = None
+
+    def _poll_nvml(self):
+        nv = self.nv
+        R = nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else nv.nvmlClocksThrottleReasonHwSlowdown
+        bits = {"hw_slowdown": R,
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0)),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0)),
+                "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0))}
+        try:
+            mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        except Exception:
+            mx = ""
+        while not self._stop:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                row = [str(sm), str(mx), ""] + ["Active" if (reasons & bits[n]) else "Not Active" for n in
+                                                ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")]
+                self.rows.append((time.monotonic(), row))
+            except Exception:
+                pass
+            time.sleep(0.05)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -116,13 +159,15 @@ class ClockSampler:
         self.t0, self.t1 = t0, t1
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            pass
+        self._stop = True
+        if self.mode == "off" or (self.mode == "smi" and self.proc is None):
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
         t0, t1 = getattr(self, "t0", None), getattr(self, "t1", None)
         rows = [r for t, r in self.rows if t0 is None or (t0 <= t <= t1 + 0.15)]
         sm = sorted(int(float(r[0])) for r in rows if r and r[0].replace(".", "").isdigit())
@@ -130,7 +175,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for r in rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": self.mode}
 
 
 # ------------------------------------------------------------------------------ CPU arm

@@ -28,6 +28,34 @@ def _gather(pooled, rows):
     return g(rows) if g is not None else pooled.index_select(0, rows)
 
 
+class _PinnedStaging:
+    """A small ring of page-locked host buffers for the per-step bookkeeping tensors (pair lists, offsets, multi-hot
+    labels).  `tensor.pin_memory()` every step goes through cudaHostAlloc whenever the caching host allocator has no free
+    block -- a driver call that can stall the enqueueing thread for tens of milliseconds; the ring allocates four slots
+    once and guards each slot with an event recorded after its asynchronous copy."""
+
+    def __init__(self, slots=4):
+        self.slots = [None] * slots
+        self.i = 0
+
+    def to_device(self, host, dev):
+        """host: 1-D CPU tensor -> device copy (asynchronous, from pinned memory)."""
+        n = host.numel()
+        k = self.i
+        self.i = (self.i + 1) % len(self.slots)
+        slot = self.slots[k]
+        if slot is None or slot[0].numel() < n or slot[0].dtype != host.dtype:
+            slot = [torch.empty((max(n, 256),), dtype=host.dtype).pin_memory(), None]
+            self.slots[k] = slot
+        if slot[1] is not None:
+            slot[1].synchronize()                      # the copy that last read this slot (4 steps ago) is long done
+        slot[0][:n].copy_(host)
+        out = slot[0][:n].to(dev, non_blocking=True)
+        slot[1] = torch.cuda.Event()
+        slot[1].record()
+        return out
+
+
 def _host_labels(target):
     lab = target.get_field("labels_host") if target.has_field("labels_host") else target.get_field("labels")
     if isinstance(lab, torch.Tensor):
@@ -96,6 +124,8 @@ class RoIRegLossComputation(object):
         self._k_cap = None
         self._k_host = None
         self._k_event = None
+        self._stage_i32 = _PinnedStaging()
+        self._stage_f32 = _PinnedStaging()
 
     def __call__(self, class_score, det_score, ref_scores, ref_bbox_preds, sim_feature, clean_pooled_feats,
                  feature_extractor, model_sim, proposals, targets, epsilon=1e-8):
@@ -118,13 +148,13 @@ class RoIRegLossComputation(object):
         offs = [0]
         for s in sizes:
             offs.append(offs[-1] + s)
-        meta = torch.tensor(pair_img + pair_cls + offs, dtype=torch.int32).pin_memory().to(dev, non_blocking=True)
+        meta = self._stage_i32.to_device(torch.tensor(pair_img + pair_cls + offs, dtype=torch.int32), dev)
         pair_img_d, pair_cls_d, img_off_d = meta[:P], meta[P:2 * P], meta[2 * P:]
         img_labels = torch.zeros((B, C), dtype=torch.float32)
         for b in range(B):
             for c in pos[b]:
                 img_labels[b, c + 1] = 1.0
-        img_labels_d = img_labels.pin_memory().to(dev, non_blocking=True)
+        img_labels_d = self._stage_f32.to_device(img_labels.view(-1), dev).view(B, C)
         boxes = torch.cat([p.bbox for p in proposals], dim=0).float().contiguous()
         Ncap = max(sizes)
         # ---- loss.py:234-259: class softmax x per-image proposal softmax, supervisors of the refinement branches
