@@ -363,3 +363,45 @@ def test_roi_pool_forward_with_fused_dropblock_copy(capi):
     assert torch.equal(buf[:R], out) and torch.equal(arg, arg0)
     assert torch.equal(sc, sc0) and torch.equal(bm, capi.dropblock_mask(cen, 3, sc0))
     assert torch.equal(buf[R:], aug)
+
+
+def test_aug_positives_builder(capi):
+    """One kernel == gather + per-segment DropBlock + `noise * x + x` + concatenation (loss.py:296-305), forward and
+    backward, with an injected noise tensor (bit-exact vs torch); with the built-in Philox noise: N(0,1) statistics,
+    same draws in forward and backward, zero padding rows."""
+    g = torch.Generator().manual_seed(21)
+    R, C, Kc = 300, 16, 40
+    seg = [0, 9, 9, 30]                                   # K = 30 real rows, 10 padding rows, an empty segment
+    K, P = seg[-1], len(seg) - 1
+    pooled = torch.randn(R, C, 7, 7, generator=g).cuda()
+    rows = torch.randint(0, R, (Kc,), generator=g).cuda()
+    cen = (torch.rand(Kc, 7, 7, generator=g) < 0.3).float().cuda()
+    noise = torch.randn(Kc, C, 7, 7, generator=g).cuda()
+    off = torch.tensor(seg, dtype=torch.int32).cuda()
+    out, sc = capi.aug_positives(pooled, rows, off, P, cen, 1, noise=noise)
+    X = pooled[rows]
+    drop_ref, _ = capi.dropblock_seg(X, cen, 1, off, P)
+    assert torch.equal(out[:K], drop_ref[:K]) and float(out[K:Kc].abs().sum()) == 0.0
+    assert torch.equal(out[Kc:Kc + K], (noise * X + X)[:K]) and float(out[Kc + K:].abs().sum()) == 0.0
+    # backward vs autograd of the same expression
+    gy = torch.randn(2 * Kc, C, 7, 7, generator=g).cuda()
+    gx, _ = capi.aug_positives(gy, rows, off, P, cen, 1, scale_seg=sc, noise=noise, backward=True)
+    Xr = X.clone().requires_grad_(True)
+    bm = (1 - cen) * 1.0
+    scale = torch.zeros(Kc, device="cuda")
+    for p in range(P):
+        if seg[p + 1] > seg[p]:
+            scale[seg[p]:seg[p + 1]] = sc[p, 1]
+    ref = torch.cat([Xr * (bm * scale[:, None, None])[:, None], noise * Xr + Xr])
+    valid = torch.zeros(2 * Kc, device="cuda"); valid[:K] = 1; valid[Kc:Kc + K] = 1
+    (ref * gy * valid[:, None, None, None]).sum().backward()
+    torch.testing.assert_close(gx, Xr.grad, rtol=1e-6, atol=1e-6)
+    # built-in noise
+    o1, sc1 = capi.aug_positives(pooled, rows, off, P, cen, 1, seed=123)
+    o2, _ = capi.aug_positives(pooled, rows, off, P, cen, 1, seed=124)
+    assert torch.equal(o1[:Kc], out[:Kc]) and not torch.equal(o1[Kc:], o2[Kc:])
+    eps = (o1[Kc:Kc + K] / X[:K] - 1).flatten()
+    assert abs(float(eps.mean())) < 0.02 and abs(float(eps.std()) - 1.0) < 0.02
+    gx1, _ = capi.aug_positives(gy, rows, off, P, cen, 1, scale_seg=sc1, seed=123, backward=True)
+    exp = gy[:K] * (bm * scale[:, None, None])[:K, None] + gy[Kc:Kc + K] * (o1[Kc:Kc + K] / X[:K])
+    torch.testing.assert_close(gx1[:K], exp, rtol=2e-4, atol=2e-4)
