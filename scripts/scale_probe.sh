@@ -7,11 +7,10 @@ run() {  # name, env, extra args
       bench.py --gpus $N --steps 10 --warmup 3 --no-cpu-baseline $3 > $OUT/$1.json 2> $OUT/$1.err
   echo "$1 rc=$?"; python -c "
 import json,sys
-d=json.load(open('$OUT/$1.json')); print('$1', 'ms/step', round(d['ms_per_step'],2), 'value', round(d['value']), 'e2e ms', round(d['e2e']['ms_per_step'],2))" 2>/dev/null || tail -3 $OUT/$1.err
+d=json.loads([l for l in open('$OUT/$1.json') if l.startswith('{')][-1]); print('$1', 'ms/step', round(d['ms_per_step'],2), 'value', round(d['value']), 'e2e ms', round(d['e2e']['ms_per_step'],2))" 2>/dev/null || tail -3 $OUT/$1.err
 }
 run n${N}_default "ODWSCL_SM_MARGIN=0" ""
-run n${N}_nosync "ODWSCL_SM_MARGIN=0" "--no-allreduce"
 run n${N}_margin8 "ODWSCL_SM_MARGIN=8" ""
 run n${N}_maxctas8 "ODWSCL_SM_MARGIN=0 NCCL_MAX_CTAS=8" ""
 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $OUT/n1.json 2> $OUT/n1.err; python -c "
-import json; d=json.load(open('$OUT/n1.json')); print('n1 ms/step', round(d['ms_per_step'],2), 'value', round(d['value']))"
+import json; d=json.loads([l for l in open('$OUT/n1.json') if l.startswith('{')][-1]); print('n1 ms/step', round(d['ms_per_step'],2), 'value', round(d['value']))"
