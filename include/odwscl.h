@@ -190,6 +190,12 @@ int odwscl_roi_pool_fwd_nhwc_aug_f32(const float* feat_nhwc, int B, int C, int H
 int odwscl_dropblock_prepare_f32(const float* centres, int R, int ph, int pw, int block, float* scale_io,
                                  float* mask_out, odwscl_stream_t stream);
 
+/* Measurement aid, not part of the path: loads every cell of every roi's clamped extent ONCE per (roi, 128-channel slab)
+ * with the pooling kernel's access pattern and reduces it with a plain max -- the time the L2 -> SM fabric charges for the
+ * bytes of a "stage the roi region once" ROIPool design.  out: R * ceil(C/128) * 7 floats. */
+int odwscl_probe_roi_stream_f32(const float* feat_nhwc, int B, int C, int H, int W, const float* rois, int R,
+                                float scale, float* out, odwscl_stream_t stream);
+
 /* ---- A6 / A7 / N1: the fully-connected block -- fc6 + fc7 (modeling/backbone/vgg16.py:122-130,148-162), Sim_Net
  * (roi_heads/sim_head/sim_net.py:10-26) and the MIST predictor heads (roi_heads/weak_head/roi_weak_predictors.py:
  * 158-165); replaces the cuBLAS GEMMs behind nn.Linear forward / backward plus the separate ReLU, Dropout and

@@ -44,6 +44,7 @@ _SIGS = {
     "odwscl_roi_pool_bwd_nhwc_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "odwscl_roi_pool_fwd_nhwc_aug_f32": (_I, [_P, _I, _I, _I, _I, _P, _I, _F, _P, _P, _P, _P, _P]),
     "odwscl_dropblock_prepare_f32": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
+    "odwscl_probe_roi_stream_f32": (_I, [_P, _I, _I, _I, _I, _P, _I, _F, _P, _P]),
     "odwscl_roi_pool_bwd_nhwc_multi_f32": (_I, [_P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "odwscl_dropblock_mask_f32": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
     "odwscl_roi_align_fwd_f32": (_I, [_P, _I, _I, _I, _I, _P, _I, _F, _I, _I, _I, _P, _P]),
@@ -242,6 +243,18 @@ def roi_pool_forward_aug(feat, rois, scale, centres, block, buf):
         _call("odwscl_roi_pool_fwd_nhwc_aug_f32", _ptr(feat), B, C, H, W, _ptr(rois), R, float(scale), _ptr(buf[:R]),
               _ptr(arg), _ptr(bmask), _ptr(buf[R:]), _stream())
     return arg, scale_io, bmask
+
+
+def probe_roi_stream(feat, rois, scale):
+    """Measurement aid (scripts/run_roipool_once.py): see odwscl_probe_roi_stream_f32."""
+    assert _is_nhwc(feat)
+    B, C, H, W = feat.shape
+    R = rois.shape[0]
+    out = torch.empty((R * ((C + 127) // 128) * 7,), dtype=torch.float32, device=feat.device)
+    with torch.cuda.device(feat.device):
+        _call("odwscl_probe_roi_stream_f32", _ptr(feat), B, C, H, W, _ptr(_chk(rois, torch.float32, "rois")), R, float(scale),
+              _ptr(out), _stream())
+    return out
 
 
 def roi_pool_backward(grad, rois, argmax, ph, pw, B, C, H, W, channels_last=False):

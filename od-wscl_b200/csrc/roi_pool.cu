@@ -176,6 +176,38 @@ static int launch_fwd_nhwc7(const float* nhwc, const float* rois, int C, int H, 
   return 0;
 }
 
+// Measurement aid: the FLOOR of any "stage the roi's region once per (roi, 128-channel slab)" design -- every
+// cell of the roi's clamped extent is loaded exactly once per slab with the same 16-byte-per-lane pattern as the pooling
+// kernel and reduced with a single FMNMX (no bins, no argmax, no 50 KB of output).  Its time is what the L2 -> SM fabric
+// charges for the bytes alone.
+__global__ void __launch_bounds__(7 * 32, 4)
+roi_stream_probe_kernel(const float4* __restrict__ feat4, const float* __restrict__ rois, int C, int H, int W, float scale,
+                        float* __restrict__ out) {
+  const int CQ = C >> 2;
+  const int n = blockIdx.x, c0 = blockIdx.y * kSlab;
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const RoiGeom g = roi_geom(rois + (size_t)n * 5, scale, 7, 7);
+  int hs, he, ws, we, t0, t1;
+  bin_range(0, g.bh, g.y1, H, hs, t0);
+  bin_range(6, g.bh, g.y1, H, t1, he);
+  bin_range(0, g.bw, g.x1, W, ws, t0);
+  bin_range(6, g.bw, g.x1, W, t1, we);
+  float m = -FLT_MAX;
+  if (4 * lane < min(kSlab, C - c0)) {
+    const float4* base = feat4 + (size_t)g.b * H * W * CQ + (c0 >> 2) + lane;
+    for (int h = hs + wid; h < he; h += 7) {                 // rows round-robin over the 7 warps
+      const float4* p = base + (size_t)(h * W + ws) * CQ;
+#pragma unroll 4
+      for (int w = ws; w < we; ++w, p += CQ) {
+        const float4 a = __ldg(p);
+        m = fmaxf(m, fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)));
+      }
+    }
+  }
+  m = odw_warp_max(m);
+  if (lane == 0) out[((size_t)n * gridDim.y + blockIdx.y) * 7 + wid] = m;
+}
+
 // one thread per output scalar, NCHW direct (any bin shape / channel count)
 __global__ void roi_pool_fwd_generic_kernel(const float* __restrict__ feat, const float* __restrict__ rois,
                                             long long total, int C, int H, int W, float scale, int PH,
@@ -446,6 +478,18 @@ ODW_API int odwscl_roi_pool_fwd_nhwc_aug_f32(const float* feat_nhwc, int B, int 
   if (R == 0 || C == 0) return 0;
   if (!feat_nhwc || !rois || !out || !argmax || !aug_mask || !out_aug) return ODWSCL_EINVAL;
   return launch_fwd_nhwc7(feat_nhwc, rois, C, H, W, R, scale, out, argmax, (cudaStream_t)stream, aug_mask, out_aug);
+}
+
+ODW_API int odwscl_probe_roi_stream_f32(const float* feat_nhwc, int B, int C, int H, int W, const float* rois, int R,
+                                        float scale, float* out, odwscl_stream_t stream) {
+  if (B < 0 || C <= 0 || H <= 0 || W <= 0 || R < 0 || (C & 3)) return ODWSCL_EINVAL;
+  if (R == 0) return 0;
+  if (!feat_nhwc || !rois || !out) return ODWSCL_EINVAL;
+  dim3 grid(R, odw_cdiv(C, kSlab));
+  roi_stream_probe_kernel<<<grid, 7 * 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(feat_nhwc), rois, C, H, W,
+                                                                    scale, out);
+  ODW_LAUNCH_CHECK();
+  return 0;
 }
 
 ODW_API int odwscl_roi_pool_bwd_nhwc_f32(const float* grad_out, const int32_t* argmax, const float* rois, int R, int B,

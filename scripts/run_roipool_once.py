@@ -25,3 +25,17 @@ for it in range(6):
     tf.append(e[0].elapsed_time(e[1])); tb.append(e[1].elapsed_time(e[2]))
 print("fwd ms", [round(t, 4) for t in tf], "bwd ms", [round(t, 4) for t in tb])
 print("done", float(out.sum()), float(g.sum()))
+# the floor of a "stage the roi region once per (roi, slab)" design: the same bytes, each cell once, a plain max
+tp = []
+for it in range(6):
+    flush.zero_()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); pr = capi.probe_roi_stream(feat, rois, 0.125); b.record()
+    torch.cuda.synchronize()
+    tp.append(a.elapsed_time(b))
+import numpy as np
+bx = rois[:, 1:].cpu().numpy()
+q = lambda v: np.floor(v * 0.125 + 0.5)
+cells = float(((q(bx[:, 2]) - q(bx[:, 0]) + 1).clip(1) * (q(bx[:, 3]) - q(bx[:, 1]) + 1).clip(1)).sum())
+gb = cells * 512 * 4 / 1e9
+print("stream probe ms", [round(t, 4) for t in tp], "bytes once per roi: %.2f GB -> %.2f TB/s" % (gb, gb / (min(tp) * 1e-3) / 1e3))
