@@ -196,6 +196,15 @@ int odwscl_dropblock_prepare_f32(const float* centres, int R, int ph, int pw, in
 int odwscl_probe_roi_stream_f32(const float* feat_nhwc, int B, int C, int H, int W, const float* rois, int R,
                                 float scale, float* out, odwscl_stream_t stream);
 
+/* ---- A5, channels-last: legacy ROIAlign (csrc/cuda/ROIAlign_cuda.cu:64-122,177-254) on an NHWC map [B,H,W,C]
+ * (C % 4 == 0), 7x7 bins, output / grad_out in the reference's [R,C,7,7] layout.  Forward: 16-byte loads serving 4
+ * channels per bilinear corner, sample weights once per (roi, bin, sample).  Backward: shared-memory accumulation of a
+ * 4-channel plane per CTA (ODWSCL_ENOWS when 16*H*W bytes exceed shared memory: use the NCHW entry point). */
+int odwscl_roi_align_fwd_nhwc_f32(const float* feat_nhwc, int B, int C, int H, int W, const float* rois, int R,
+                                  float scale, int sampling_ratio, float* out, odwscl_stream_t stream);
+int odwscl_roi_align_bwd_nhwc_f32(const float* grad_out, const float* rois, int R, float scale, int B, int C, int H,
+                                  int W, int sampling_ratio, float* grad_in_nhwc, odwscl_stream_t stream);
+
 /* ---- A6 / A7 / N1: the fully-connected block -- fc6 + fc7 (modeling/backbone/vgg16.py:122-130,148-162), Sim_Net
  * (roi_heads/sim_head/sim_net.py:10-26) and the MIST predictor heads (roi_heads/weak_head/roi_weak_predictors.py:
  * 158-165); replaces the cuBLAS GEMMs behind nn.Linear forward / backward plus the separate ReLU, Dropout and

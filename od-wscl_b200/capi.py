@@ -23,7 +23,7 @@ _LAUNCHES = {
     "odwscl_roi_pool_fwd_f32": 2, "odwscl_roi_pool_bwd_f32": 1, "odwscl_roi_pool_fwd_nhwc_f32": 1,
     "odwscl_roi_pool_bwd_nhwc_f32": 1, "odwscl_roi_pool_bwd_nhwc_multi_f32": 1, "odwscl_roi_pool_fwd_nhwc_aug_f32": 1,
     "odwscl_dropblock_prepare_f32": 3, "odwscl_roi_align_fwd_f32": 1,
-    "odwscl_roi_align_bwd_f32": 1, "odwscl_box_iou_f32": 1, "odwscl_nms_f32": 1, "odwscl_nms_legacy_f32": 1,
+    "odwscl_roi_align_bwd_f32": 1, "odwscl_roi_align_fwd_nhwc_f32": 1, "odwscl_roi_align_bwd_nhwc_f32": 1, "odwscl_box_iou_f32": 1, "odwscl_nms_f32": 1, "odwscl_nms_legacy_f32": 1,
     "odwscl_discover_phase_a_f32": 2, "odwscl_discover_phase_b_f32": 2, "odwscl_bank_assemble": 1,
     "odwscl_supcon_fwd_f32": 2, "odwscl_supcon_bwd_f32": 1, "odwscl_od_layer_f32": 1,
     "odwscl_dropblock_f32": 3, "odwscl_dropblock_rows_f32": 3, "odwscl_dropblock_seg_f32": 2, "odwscl_dropblock_mask_f32": 1, "odwscl_sim_nxn_f32": 2, "odwscl_gemm_nt_tf32": 1,
@@ -49,6 +49,8 @@ _SIGS = {
     "odwscl_dropblock_mask_f32": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
     "odwscl_roi_align_fwd_f32": (_I, [_P, _I, _I, _I, _I, _P, _I, _F, _I, _I, _I, _P, _P]),
     "odwscl_roi_align_bwd_f32": (_I, [_P, _P, _I, _F, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "odwscl_roi_align_fwd_nhwc_f32": (_I, [_P, _I, _I, _I, _I, _P, _I, _F, _I, _P, _P]),
+    "odwscl_roi_align_bwd_nhwc_f32": (_I, [_P, _P, _I, _F, _I, _I, _I, _I, _I, _P, _P]),
     "odwscl_box_iou_f32": (_I, [_P, _I, _P, _I, _I, _P, _P]),
     "odwscl_nms_f32": (_I, [_P, _P, _I, _F, _P, _P, _P]),
     "odwscl_nms_legacy_f32": (_I, [_P, _P, _I, _F, _P, _P, _P]),
@@ -308,8 +310,15 @@ def roi_pool_backward_multi(grad, grad2, srows, sgrad, rois, argmax, B, C, H, W,
 
 
 def roi_align_forward(feat, rois, scale, ph, pw, sampling_ratio):
-    feat, rois = _chk(feat, torch.float32, "input"), _chk(rois, torch.float32, "rois")
+    rois = _chk(rois, torch.float32, "rois")
     B, C, H, W = feat.shape
+    if _is_nhwc(feat) and (ph, pw) == (7, 7) and C % 4 == 0 and feat.dtype == torch.float32 and feat.is_cuda:
+        out = torch.empty((rois.shape[0], C, 7, 7), dtype=torch.float32, device=feat.device)
+        with torch.cuda.device(feat.device):       # memory is [B,H,W,C]: the channels-last kernel, no transpose
+            _call("odwscl_roi_align_fwd_nhwc_f32", _ptr(feat), B, C, H, W, _ptr(rois), rois.shape[0], float(scale),
+                  int(sampling_ratio), _ptr(out), _stream())
+        return out
+    feat = _chk(feat, torch.float32, "input")
     out = torch.empty((rois.shape[0], C, ph, pw), dtype=torch.float32, device=feat.device)
     with torch.cuda.device(feat.device):
         _call("odwscl_roi_align_fwd_f32", _ptr(feat), B, C, H, W, _ptr(rois), rois.shape[0], float(scale), ph, pw,
@@ -317,8 +326,14 @@ def roi_align_forward(feat, rois, scale, ph, pw, sampling_ratio):
     return out
 
 
-def roi_align_backward(grad, rois, scale, ph, pw, B, C, H, W, sampling_ratio):
+def roi_align_backward(grad, rois, scale, ph, pw, B, C, H, W, sampling_ratio, channels_last=False):
     grad, rois = _chk(grad, torch.float32, "grad"), _chk(rois, torch.float32, "rois")
+    if channels_last and (ph, pw) == (7, 7) and C % 4 == 0 and H * W * 16 <= 220 * 1024:
+        gin = torch.empty((B, H, W, C), dtype=torch.float32, device=grad.device)
+        with torch.cuda.device(grad.device):
+            _call("odwscl_roi_align_bwd_nhwc_f32", _ptr(grad), _ptr(rois), rois.shape[0], float(scale), B, C, H, W,
+                  int(sampling_ratio), _ptr(gin), _stream())
+        return gin.permute(0, 3, 1, 2)
     gin = torch.empty((B, C, H, W), dtype=torch.float32, device=grad.device)
     with torch.cuda.device(grad.device):
         _call("odwscl_roi_align_bwd_f32", _ptr(grad), _ptr(rois), rois.shape[0], float(scale), ph, pw, B, C, H, W,

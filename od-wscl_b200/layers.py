@@ -187,6 +187,7 @@ class _ROIAlign(Function):
         ctx.spatial_scale = spatial_scale
         ctx.sampling_ratio = sampling_ratio
         ctx.input_shape = input.size()
+        ctx.channels_last = capi._is_nhwc(input)      # conv stack output: the channels-last kernels, grad in the same layout
         return _C.roi_align_forward(input, roi, spatial_scale, ctx.output_size[0], ctx.output_size[1], sampling_ratio)
 
     @staticmethod
@@ -194,8 +195,12 @@ class _ROIAlign(Function):
     def backward(ctx, grad_output):
         (rois,) = ctx.saved_tensors
         bs, ch, h, w = ctx.input_shape
-        grad_input = _C.roi_align_backward(grad_output, rois, ctx.spatial_scale, ctx.output_size[0],
-                                           ctx.output_size[1], bs, ch, h, w, ctx.sampling_ratio)
+        if ctx.channels_last:
+            grad_input = capi.roi_align_backward(grad_output, rois, ctx.spatial_scale, ctx.output_size[0], ctx.output_size[1],
+                                                 bs, ch, h, w, ctx.sampling_ratio, channels_last=True)
+        else:
+            grad_input = _C.roi_align_backward(grad_output, rois, ctx.spatial_scale, ctx.output_size[0],
+                                               ctx.output_size[1], bs, ch, h, w, ctx.sampling_ratio)
         return grad_input, None, None, None, None
 
 

@@ -145,6 +145,40 @@ def test_roi_align_golden(capi, golden, tag):
     np.testing.assert_allclose(gi.cpu().numpy(), G[tag + "_grad_in"], rtol=1e-4, atol=1e-5)
 
 
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_roi_align_golden_channels_last(capi, golden, tag):
+    """The same reference-generated vectors through the channels-last kernels (NHWC forward, plane-centric backward)."""
+    G = golden("roi_align.npz")
+    sr = int(G[tag + "_sr"])
+    feat = cu(G[tag + "_feat"])
+    B, C, H, W = feat.shape
+    if C % 4:
+        pytest.skip("channels-last path needs C % 4 == 0")
+    out = capi.roi_align_forward(feat.contiguous(memory_format=torch.channels_last), cu(G[tag + "_rois"]), 0.125, 7, 7, sr)
+    np.testing.assert_allclose(out.cpu().numpy(), G[tag + "_out"], rtol=1e-5, atol=1e-5)
+    gi = capi.roi_align_backward(cu(G[tag + "_grad_out"]), cu(G[tag + "_rois"]), 0.125, 7, 7, B, C, H, W, sr, channels_last=True)
+    np.testing.assert_allclose(gi.contiguous().cpu().numpy(), G[tag + "_grad_in"], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("B,C,H,W,R,sr", [(2, 64, 38, 50, 300, 0), (1, 128, 76, 128, 120, 2), (2, 8, 20, 31, 64, 0)])
+def test_roi_align_channels_last_vs_oracle(capi, B, C, H, W, R, sr):
+    """Larger random cases (adaptive sampling grids on big rois, rois partly outside the map, sampling_ratio 0 and 2)
+    against the CPU oracle (csrc/cuda/ROIAlign_cuda.cu:64-122,177-254 restated in oracle/odwscl_oracle.c), both layouts."""
+    g = torch.Generator().manual_seed(R + sr)
+    feat = torch.randn(B, C, H, W, generator=g)
+    rois = _rand_rois(g, B, H, W, R)
+    go = torch.randn(R, C, 7, 7, generator=g)
+    exp = orc.roi_align_forward(feat.numpy(), rois.numpy(), 0.125, 7, 7, sr)
+    exp_gi = orc.roi_align_backward(go.numpy(), rois.numpy(), 0.125, B, C, H, W, sr)
+    scale = float(np.abs(exp_gi).max())
+    for cl in (True, False):
+        f = feat.cuda().contiguous(memory_format=torch.channels_last) if cl else feat.cuda()
+        out = capi.roi_align_forward(f, rois.cuda(), 0.125, 7, 7, sr)
+        np.testing.assert_allclose(out.cpu().numpy(), exp, rtol=1e-5, atol=2e-5)
+        gi = capi.roi_align_backward(go.cuda(), rois.cuda(), 0.125, 7, 7, B, C, H, W, sr, channels_last=cl)
+        np.testing.assert_allclose(gi.contiguous().cpu().numpy(), exp_gi, rtol=1e-4, atol=2e-5 * scale + 1e-6)
+
+
 # ------------------------------------------------------------------------------- IoU / NMS
 def test_iou_nms_golden(capi, golden):
     G = golden("boxes.npz")
