@@ -41,7 +41,12 @@ def wrap_ddp(model, device=None):
     ids = [device.index] if device is not None and device.type == "cuda" else None
     if ids is not None:
         from . import capi
-        capi.set_sm_margin(int(os.environ.get("ODWSCL_SM_MARGIN", "0")))      # SMs left to the NCCL all-reduce kernels
+        # SMs left to the NCCL all-reduce kernels.  The persistent conv / fc kernels otherwise occupy every SM (1 CTA per SM,
+        # ~200 KB of shared memory each, so an NCCL CTA cannot co-reside); NCCL then grabs SMs between two of our launches
+        # and the NEXT persistent grid no longer fits: its last CTAs -- and the split-K slices spinning on them -- wait for
+        # the 411 MB fc6 bucket to finish.  Measured at 2 GPUs: steps of 37 / 67 / 131 ms among 17.8 ms ones with margin 0,
+        # a flat 18.2-19.1 ms with margin 8 (profiles/r02_scaling.md).
+        capi.set_sm_margin(int(os.environ.get("ODWSCL_SM_MARGIN", "8")))
     # 611 MB of fp32 gradients per step: large buckets (NVSwitch collectives are latency-, not link-bound) and gradients
     # stored as views of the buckets (no 611 MB grad -> bucket copy before each all-reduce)
     return torch.nn.parallel.DistributedDataParallel(model, device_ids=ids, broadcast_buffers=False,

@@ -9,11 +9,7 @@ run() {  # name, env, extra args
 import json,sys
 d=json.loads([l for l in open('$OUT/$1.json') if l.startswith('{')][-1]); print('$1', 'ms/step', round(d['ms_per_step'],2), 'value', round(d['value']), 'e2e ms', round(d['e2e']['ms_per_step'],2))" 2>/dev/null || tail -3 $OUT/$1.err
 }
-run n${N}_default "ODWSCL_SM_MARGIN=0" ""
-run n${N}_margin8 "ODWSCL_SM_MARGIN=8" ""
-run n${N}_margin16 "ODWSCL_SM_MARGIN=16" ""
-run n${N}_maxctas4 "ODWSCL_SM_MARGIN=0 NCCL_MAX_CTAS=4" ""
-run n${N}_maxctas4_margin4 "ODWSCL_SM_MARGIN=4 NCCL_MAX_CTAS=4" ""
+for m in ${MARGINS:-8 16}; do run n${N}_margin$m "ODWSCL_SM_MARGIN=$m" ""; done
 for f in $OUT/n${N}_*.err; do echo $f; grep "resident per-step" $f | cut -c1-160; done
 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $OUT/n1.json 2> $OUT/n1.err; python -c "
 import json; d=json.loads([l for l in open('$OUT/n1.json') if l.startswith('{')][-1]); print('n1 ms/step', round(d['ms_per_step'],2), 'value', round(d['value']))"
