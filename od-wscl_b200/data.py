@@ -114,3 +114,80 @@ class HostPrefetcher:
             t.record_stream(cur)
         self.pending = None
         return dev
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# N3 remainder: proposal file -> per-image proposals, scale selection, image resize, one training example
+def resize_size(image_size, min_size, max_size, pick=None):
+    """Resize.get_size (data/transforms/transforms.py:42-64): target (height, width) for an image of (width, height).
+    min_size: int or sequence (multi-scale: one is drawn per image, `pick` = the drawn value for replay)."""
+    import random
+    w, h = image_size
+    if not isinstance(min_size, (list, tuple)):
+        min_size = (min_size,)
+    size = pick if pick is not None else random.choice(min_size)
+    if max_size is not None:
+        mn, mx = float(min((w, h))), float(max((w, h)))
+        if mx / mn * size > max_size:
+            size = int(round(max_size * mn / mx))
+    if (w <= h and w == size) or (h <= w and h == size):
+        return (h, w)
+    if w < h:
+        return (int(size * h / w), size)
+    return (size, int(size * w / h))
+
+
+def resize_image(img, size_hw):
+    """torchvision.transforms.functional.resize on a PIL image as the reference calls it (transforms.py:68): bilinear."""
+    from PIL import Image
+    return img.resize((size_hw[1], size_hw[0]), Image.BILINEAR)
+
+
+def image_to_tensor(img):
+    """torchvision ToTensor (transforms.py:113-115): PIL RGB uint8 -> float32 [3,H,W] in [0,1]."""
+    a = np.asarray(img, dtype=np.uint8)
+    if a.ndim == 2:
+        a = a[:, :, None].repeat(3, axis=2)
+    return torch.from_numpy(np.ascontiguousarray(a.transpose(2, 0, 1))).float().div(255)
+
+
+class ProposalFile:
+    """The pickled proposal file of the reference (`{'boxes': [ndarray per image], 'indexes' | 'ids': [image id ...],
+    'scores': ...}`; data/datasets/voc.py:62-66,87-111): per-image lookup + the unique / clip / min-size filter."""
+
+    def __init__(self, path_or_dict):
+        if isinstance(path_or_dict, dict):
+            self.data = path_or_dict
+        else:
+            import pickle
+            with open(path_or_dict, "rb") as f:
+                self.data = pickle.load(f, encoding="latin1")
+        self.id_field = "indexes" if "indexes" in self.data else "ids"          # compat fix, voc.py:93
+        self._pos = {int(i): k for k, i in enumerate(self.data[self.id_field])}
+
+    def __len__(self):
+        return len(self._pos)
+
+    def rois(self, image_id, width, height, min_size=20):
+        """float32 [n,4] xyxy proposals of one image as the dataset hands them to the transforms (voc.py:94-111)."""
+        return filter_proposals(self.data["boxes"][self._pos[int(image_id)]], width, height, min_size)
+
+
+def prepare_example(img, rois, min_size, max_size, flip, pick=None, target_boxes=None):
+    """One training example through build_transforms(is_train=True) (data/transforms/build.py): Resize -> horizontal flip
+    (the caller draws `flip`) -> ToTensor -> Normalize(to_bgr255).  img: PIL RGB; rois / target_boxes: float32 [n,4] in
+    the original image.  Returns (image [3,h,w] float32, rois, target_boxes, (w, h))."""
+    from PIL import Image
+    w0, h0 = img.size
+    size_hw = resize_size((w0, h0), min_size, max_size, pick)
+    img = resize_image(img, size_hw)
+    w1, h1 = img.size
+    rois = resize_boxes(rois, (w0, h0), (w1, h1))
+    if target_boxes is not None:
+        target_boxes = resize_boxes(target_boxes, (w0, h0), (w1, h1))
+    if flip:
+        img = img.transpose(Image.FLIP_LEFT_RIGHT)
+        rois = hflip_boxes(rois, w1)
+        if target_boxes is not None:
+            target_boxes = hflip_boxes(target_boxes, w1)
+    return normalize_image(image_to_tensor(img)), rois, target_boxes, (w1, h1)

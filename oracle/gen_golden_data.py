@@ -112,10 +112,61 @@ def gen_tta():
     print("wrote", path)
 
 
+def gen_input_pipeline():
+    """N3 remainder: Resize.get_size, the whole train transform chain and the proposal lookup of PascalVOCDataset, from
+    the reference's own classes (data/transforms/transforms.py, data/datasets/voc.py:87-111)."""
+    ref_shims.install()
+    from PIL import Image
+    from wetectron.data.transforms import transforms as T
+    from wetectron.data.datasets.coco import unique_boxes
+    from wetectron.structures.bounding_box import BoxList
+    from wetectron.structures.boxlist_ops import remove_small_boxes
+    out = {}
+    # (1) get_size over shapes x scales (random.choice replaced by a 1-element tuple per call)
+    cases = []
+    for (w, h) in ((500, 375), (375, 500), (333, 500), (500, 500), (1000, 240), (640, 480)):
+        for s in (480, 576, 688, 864, 1200, 600):
+            for mx in (2000, 1000):
+                oh, ow = T.Resize(s, mx).get_size((w, h))
+                cases.append([w, h, s, mx, oh, ow])
+    out["get_size"] = np.array(cases)
+    # (2) one example through Resize -> RandomHorizontalFlip(prob 1 / 0) -> ToTensor -> Normalize
+    rs = np.random.RandomState(5)
+    arr = rs.randint(0, 256, size=(75, 100, 3), dtype=np.uint8)
+    out["img_u8"] = arr
+    raw = np.stack([rs.uniform(0, 70, 60), rs.uniform(0, 45, 60), rs.uniform(0, 70, 60) + 29, rs.uniform(0, 45, 60) + 29], 1).round().astype(np.float32)
+    raw[7] = raw[3]
+    out["raw_rois"] = raw
+    ids = [11, 42, 7]
+    prop = {"boxes": [raw[::2], raw, raw[5:25]], "indexes": ids}
+    for k, i in enumerate(ids):
+        out["prop_boxes_%d" % k] = prop["boxes"][k]
+    out["prop_ids"] = np.array(ids)
+    # dataset lookup + filter (voc.py:87-111) for image id 42 on a 100x75 image
+    rois = prop["boxes"][prop["indexes"].index(42)]
+    rois = rois[unique_boxes(rois), :]
+    bl = BoxList(torch.tensor(rois.astype(np.float64)), (100, 75), mode="xyxy").clip_to_image(remove_empty=True)
+    bl = remove_small_boxes(boxlist=bl, min_size=20)
+    out["lookup_42"] = bl.bbox.numpy()
+    for tag, flip in (("flip", 1.0), ("noflip", 0.0)):
+        tf = T.Compose([T.Resize(120, 400), T.RandomHorizontalFlip(flip), T.ToTensor(),
+                        T.Normalize(mean=[102.9801, 115.9465, 122.7717], std=[1.0, 1.0, 1.0], to_bgr255=True)])
+        img = Image.fromarray(arr, "RGB")
+        tgt = BoxList(torch.tensor([[10., 12., 60., 50.]]), img.size, mode="xyxy")
+        im, tg, ro = tf(img, tgt, BoxList(bl.bbox.clone(), img.size, mode="xyxy"))
+        out["ex_%s_img" % tag], out["ex_%s_rois" % tag], out["ex_%s_tgt" % tag] = im.numpy(), ro.bbox.numpy(), tg.bbox.numpy()
+        out["ex_%s_size" % tag] = np.array(ro.size)
+    path = os.path.join(ROOT, "tests", "golden", "input_pipeline.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, {k: np.asarray(v).shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     if "--tta" in sys.argv:
         gen_tta()
     elif "--postprocess" in sys.argv:
         gen_postprocess()
+    elif "--input" in sys.argv:
+        gen_input_pipeline()
     else:
         main()

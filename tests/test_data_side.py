@@ -49,3 +49,37 @@ def test_host_prefetcher_round_trip():
         if i + 1 < 4:
             pf.feed(a[i + 1])
         assert torch.equal(d.cpu(), a[i])
+
+
+def test_scale_selection_matches_reference(golden):
+    """Resize.get_size (transforms.py:42-64) over portrait / landscape / square / panoramic shapes x the multi-scale set."""
+    G = golden("input_pipeline.npz")
+    for w, h, s, mx, oh, ow in G["get_size"].tolist():
+        assert data.resize_size((w, h), s, mx) == (oh, ow), (w, h, s, mx)
+    assert data.resize_size((500, 375), (480, 576, 688), 2000, pick=576) == (576, 768)
+
+
+def test_proposal_file_and_example_pipeline_match_reference(golden, tmp_path):
+    """Pickled proposal file -> per-image lookup + filter (voc.py:87-111), then Resize -> flip -> ToTensor -> Normalize
+    (build_transforms) on a PIL image: bit-exact against the reference's own dataset / transform classes."""
+    import pickle
+    from PIL import Image
+    G = golden("input_pipeline.npz")
+    prop = {"boxes": [G["prop_boxes_%d" % k] for k in range(3)], "indexes": [int(i) for i in G["prop_ids"]]}
+    path = tmp_path / "proposals.pkl"
+    with open(path, "wb") as f:
+        pickle.dump(prop, f)
+    pf = data.ProposalFile(str(path))
+    assert len(pf) == 3
+    rois = pf.rois(42, 100, 75)
+    assert np.array_equal(rois.numpy(), G["lookup_42"])
+    legacy = data.ProposalFile({"boxes": prop["boxes"], "ids": prop["indexes"]})          # the 'ids' spelling
+    assert np.array_equal(legacy.rois(42, 100, 75).numpy(), G["lookup_42"])
+    img = Image.fromarray(G["img_u8"], "RGB")
+    tgt = torch.tensor([[10., 12., 60., 50.]])
+    for tag, flip in (("flip", True), ("noflip", False)):
+        im, ro, tg, size = data.prepare_example(img, rois, 120, 400, flip, target_boxes=tgt)
+        assert list(size) == G["ex_%s_size" % tag].tolist()
+        assert np.array_equal(im.numpy(), G["ex_%s_img" % tag])
+        assert np.array_equal(ro.numpy(), G["ex_%s_rois" % tag])
+        assert np.array_equal(tg.numpy(), G["ex_%s_tgt" % tag])
