@@ -35,6 +35,40 @@ def rank_seed(base, rank, images_per_rank):
     return base + rank * images_per_rank
 
 
+class _BackwardBegins(torch.autograd.Function):
+    """Identity on a loss tensor whose backward runs FIRST in the backward pass and switches the SM margin on: the NCCL
+    gradient all-reduce only runs beside the backward kernels, so the forward keeps every SM."""
+
+    @staticmethod
+    def forward(ctx, x, margin):
+        ctx.margin = margin
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import capi
+        capi.set_sm_margin(ctx.margin)
+        return g, None
+
+
+class MarginedDDP(torch.nn.parallel.DistributedDataParallel):
+    """DDP whose forward runs with all SMs (margin 0) and whose backward leaves `sm_margin` SMs to NCCL."""
+
+    def __init__(self, *a, sm_margin=0, **k):
+        super().__init__(*a, **k)
+        self.sm_margin = sm_margin
+
+    def forward(self, *a, **k):
+        from . import capi
+        capi.set_sm_margin(0)
+        out = super().forward(*a, **k)
+        if self.sm_margin > 0 and torch.is_grad_enabled() and isinstance(out, tuple) and isinstance(out[0], dict):
+            losses = {n: (_BackwardBegins.apply(v, self.sm_margin) if torch.is_tensor(v) and v.requires_grad else v)
+                      for n, v in out[0].items()}
+            out = (losses,) + tuple(out[1:])
+        return out
+
+
 def wrap_ddp(model, device=None):
     """DDP exactly as the reference wraps it (tools/train_net.py:50-55: broadcast_buffers=False), with
     static_graph instead of find_unused_parameters -- every parameter receives a gradient on this path."""
@@ -46,12 +80,13 @@ def wrap_ddp(model, device=None):
         # and the NEXT persistent grid no longer fits: its last CTAs -- and the split-K slices spinning on them -- wait for
         # the 411 MB fc6 bucket to finish.  Measured at 2 GPUs: steps of 37 / 67 / 131 ms among 17.8 ms ones with margin 0,
         # a flat 18.2-19.1 ms with margin 8 (profiles/r02_scaling.md).
-        capi.set_sm_margin(int(os.environ.get("ODWSCL_SM_MARGIN", "8")))
+        margin = int(os.environ.get("ODWSCL_SM_MARGIN", "8"))
+    else:
+        margin = 0
     # 611 MB of fp32 gradients per step: large buckets (NVSwitch collectives are latency-, not link-bound) and gradients
-    # stored as views of the buckets (no 611 MB grad -> bucket copy before each all-reduce)
-    return torch.nn.parallel.DistributedDataParallel(model, device_ids=ids, broadcast_buffers=False,
-                                                     static_graph=True, bucket_cap_mb=128,
-                                                     gradient_as_bucket_view=True)
+    # stored as views of the buckets
+    return MarginedDDP(model, device_ids=ids, broadcast_buffers=False, static_graph=True, bucket_cap_mb=128,
+                       gradient_as_bucket_view=True, sm_margin=margin)
 
 
 def max_over_ranks(value, device):
