@@ -427,7 +427,12 @@ def run_ours(args):
             print("[bench] %s per-step ms: %s" % (tag, [round(evs[i].elapsed_time(evs[i + 1]), 2) for i in range(n)]),
                   file=sys.stderr, flush=True)
             print("[bench] %s host enqueue ms: %s  K bound: %s" % (tag, host_ms, caps), file=sys.stderr, flush=True)
-        return sharding.max_over_ranks(evs[0].elapsed_time(evs[n]), dev)
+        mine = evs[0].elapsed_time(evs[n])
+        if world > 1 and tag:
+            per_rank = sharding.all_ranks(mine / n, dev)
+            if rank == 0:
+                print("[bench] %s ms/step per rank: %s" % (tag, [round(x, 2) for x in per_rank]), file=sys.stderr, flush=True)
+        return sharding.max_over_ranks(mine, dev)
 
     for bt in batches:
         bt["images_d"] = bt["images_h"].to(dev, non_blocking=True)

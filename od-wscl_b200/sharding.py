@@ -97,6 +97,16 @@ def max_over_ranks(value, device):
     return float(t.item())
 
 
+def all_ranks(value, device):
+    """Every rank's value (diagnosis: which part of a multi-GPU step time is the slowest GPU's clock)."""
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return [float(value)]
+    t = torch.tensor([float(value)], device=device)
+    out = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return [float(x.item()) for x in out]
+
+
 def proposals_per_step(world, images_per_rank, proposals_per_image):
     """Units all ranks process in one step (weak scaling: per-rank work is fixed)."""
     return world * images_per_rank * proposals_per_image
