@@ -630,7 +630,8 @@ def run_ours(args):
             "config": {"workload": WORKLOAD,
                        "images_per_gpu": B_PER_GPU, "proposals_per_image": N_PROP, "parallelism": "dp%d" % world,
                        "host_syncs_per_step": 1 if args.sync_k else 0, "skipped_updates": [skipped, skipped_e2e],
-                       "allreduce": not args.no_allreduce, "sm_margin": int(os.environ.get("ODWSCL_SM_MARGIN", "0")),
+                       "allreduce": not args.no_allreduce, "sm_margin": int(os.environ.get("ODWSCL_SM_MARGIN", "8")) if world > 1 else 0,
+                       "bucket_mb": int(os.environ.get("ODWSCL_BUCKET_MB", "128")) if world > 1 else None,
                        "calibration_steps": n_calib, "first_window_with_skipped_update": first_window,
                        "lr": LR, "final_loss": float(loss_h[0]),
                        "l2": "per-step working set (>=1.6 GB of activations) exceeds the 126 MB L2; kernel-alone timings flush L2 with a 256 MB write"},

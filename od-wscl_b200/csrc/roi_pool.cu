@@ -17,6 +17,8 @@
 // Backward: grad_in is zeroed, then one thread per output scalar issues a fire-and-forget
 // red.global.add.f32 at argmax (same arithmetic as the reference, :100-105).
 #include "common.cuh"
+#include <stdlib.h>
+#include <string.h>
 
 namespace {
 
@@ -74,8 +76,14 @@ constexpr int kBins = 49;
   if (v.z > m2) { m2 = v.z; i2 = (id); }    \
   if (v.w > m3) { m3 = v.w; i3 = (id); }
 
+#define ODW_RP_CMP4N(v, id)                 \
+  if (v.x > n0) { n0 = v.x; j0 = (id); }    \
+  if (v.y > n1) { n1 = v.y; j1 = (id); }    \
+  if (v.z > n2) { n2 = v.z; j2 = (id); }    \
+  if (v.w > n3) { n3 = v.w; j3 = (id); }
+
 // CQT = C/4 as a compile-time constant (cell stride becomes an immediate load offset), 0 = runtime C.
-template <int CQT>
+template <int CQT, bool kPair>
 __global__ void __launch_bounds__(7 * 32, 4)
 roi_pool_fwd_nhwc7_kernel(const float4* __restrict__ feat4, const float* __restrict__ rois, int C,
                           int H, int W, float scale, float* __restrict__ out,
@@ -105,8 +113,43 @@ roi_pool_fwd_nhwc7_kernel(const float4* __restrict__ feat4, const float* __restr
       m0 = m1 = m2 = m3 = empty ? 0.f : -FLT_MAX;
       int i0 = -1, i1 = -1, i2 = -1, i3 = -1;
       const int nw = we - ws;
+      int h = hs;
+      if (kPair) {
+        // Two rows in flight: 4 outstanding 16-byte loads per lane instead of 2.  The kernel is bound by L2 latency x loads in
+        // flight (a bin row is only ~5 cells).  Row h+1 scans into its own (n, j) and is merged with the same
+        // strict '>' afterwards, so the winner is still the first cell in row-major order that attains the maximum.
 #pragma unroll 1
-      for (int h = hs; h < he; ++h) {          // reference scan order: rows, then columns, strict '>'
+        for (; h + 1 < he; h += 2) {
+          int idx = h * W + ws;
+          const float4* p = base + (size_t)idx * CQ;
+          const float4* p2 = p + (size_t)W * CQ;
+          float n0, n1, n2, n3;
+          n0 = n1 = n2 = n3 = -FLT_MAX;
+          int j0 = -1, j1 = -1, j2 = -1, j3 = -1;
+          int k = nw;
+#pragma unroll 1
+          for (; k >= 2; k -= 2) {
+            const float4 a = __ldg(p), b = __ldg(p + CQ), c = __ldg(p2), d = __ldg(p2 + CQ);
+            p += 2 * CQ; p2 += 2 * CQ;
+            ODW_RP_CMP4(a, idx);
+            ODW_RP_CMP4(b, idx + 1);
+            ODW_RP_CMP4N(c, idx + W);
+            ODW_RP_CMP4N(d, idx + W + 1);
+            idx += 2;
+          }
+          if (k > 0) {
+            const float4 a = __ldg(p), c = __ldg(p2);
+            ODW_RP_CMP4(a, idx);
+            ODW_RP_CMP4N(c, idx + W);
+          }
+          if (n0 > m0) { m0 = n0; i0 = j0; }
+          if (n1 > m1) { m1 = n1; i1 = j1; }
+          if (n2 > m2) { m2 = n2; i2 = j2; }
+          if (n3 > m3) { m3 = n3; i3 = j3; }
+        }
+      }
+#pragma unroll 1
+      for (; h < he; ++h) {                    // reference scan order: rows, then columns, strict '>'
         int idx = h * W + ws;
         const float4* p = base + (size_t)idx * CQ;
         int k = nw;
@@ -159,21 +202,40 @@ roi_pool_fwd_nhwc7_kernel(const float4* __restrict__ feat4, const float* __restr
   }
 }
 
+
+static bool rp_pairs() {                                     // ODWSCL_ROIPOOL=rows: the one-row-at-a-time scan (A/B aid)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ODWSCL_ROIPOOL");
+    v = (e && !strcmp(e, "rows")) ? 0 : 1;
+  }
+  return v == 1;
+}
+
+template <typename K>
+static int launch_rp(K kern, dim3 grid, int smem, cudaStream_t st, const float4* f4, const float* rois, int C, int H, int W,
+                     float scale, float* out, int32_t* argmax, const float* aug_mask, float* out_aug) {
+  ODW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  kern<<<grid, 7 * 32, smem, st>>>(f4, rois, C, H, W, scale, out, argmax, aug_mask, out_aug);
+  ODW_LAUNCH_CHECK();
+  return 0;
+}
+
 static int launch_fwd_nhwc7(const float* nhwc, const float* rois, int C, int H, int W, int R, float scale,
                             float* out, int32_t* argmax, cudaStream_t st, const float* aug_mask = nullptr,
                             float* out_aug = nullptr) {
   const int smem = kSlab * kBins * (int)(sizeof(float) + sizeof(int));
   dim3 grid(R, odw_cdiv(C, kSlab));
   const float4* f4 = reinterpret_cast<const float4*>(nhwc);
+#define ODW_RP_GO(CQT_, P_) \
+  return launch_rp(roi_pool_fwd_nhwc7_kernel<CQT_, P_>, grid, smem, st, f4, rois, C, H, W, scale, out, argmax, aug_mask, out_aug)
   if (C == 512) {
-    ODW_CUDA(cudaFuncSetAttribute(roi_pool_fwd_nhwc7_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    roi_pool_fwd_nhwc7_kernel<128><<<grid, 7 * 32, smem, st>>>(f4, rois, C, H, W, scale, out, argmax, aug_mask, out_aug);
-  } else {
-    ODW_CUDA(cudaFuncSetAttribute(roi_pool_fwd_nhwc7_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    roi_pool_fwd_nhwc7_kernel<0><<<grid, 7 * 32, smem, st>>>(f4, rois, C, H, W, scale, out, argmax, aug_mask, out_aug);
+    if (rp_pairs()) ODW_RP_GO(128, true);
+    ODW_RP_GO(128, false);
   }
-  ODW_LAUNCH_CHECK();
-  return 0;
+  if (rp_pairs()) ODW_RP_GO(0, true);
+  ODW_RP_GO(0, false);
+#undef ODW_RP_GO
 }
 
 // Measurement aid: the FLOOR of any "stage the roi's region once per (roi, 128-channel slab)" design -- every
@@ -486,7 +548,10 @@ ODW_API int odwscl_probe_roi_stream_f32(const float* feat_nhwc, int B, int C, in
   if (R == 0) return 0;
   if (!feat_nhwc || !rois || !out) return ODWSCL_EINVAL;
   dim3 grid(R, odw_cdiv(C, kSlab));
-  roi_stream_probe_kernel<<<grid, 7 * 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(feat_nhwc), rois, C, H, W,
+  const char* e = getenv("ODWSCL_PROBE_SMEM");               // carve shared memory out of L1 like the pooling kernel does
+  const int smem = e ? atoi(e) : 0;
+  if (smem > 0) ODW_CUDA(cudaFuncSetAttribute(roi_stream_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  roi_stream_probe_kernel<<<grid, 7 * 32, smem, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(feat_nhwc), rois, C, H, W,
                                                                     scale, out);
   ODW_LAUNCH_CHECK();
   return 0;

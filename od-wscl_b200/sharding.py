@@ -85,7 +85,8 @@ def wrap_ddp(model, device=None):
         margin = 0
     # 611 MB of fp32 gradients per step: large buckets (NVSwitch collectives are latency-, not link-bound) and gradients
     # stored as views of the buckets
-    return MarginedDDP(model, device_ids=ids, broadcast_buffers=False, static_graph=True, bucket_cap_mb=128,
+    bucket_mb = int(os.environ.get("ODWSCL_BUCKET_MB", "128"))
+    return MarginedDDP(model, device_ids=ids, broadcast_buffers=False, static_graph=True, bucket_cap_mb=bucket_mb,
                        gradient_as_bucket_view=True, sm_margin=margin)
 
 
