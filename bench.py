@@ -338,6 +338,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        sharding.configure_nccl()
         dist.init_process_group("nccl", device_id=dev)
     torch.backends.cuda.matmul.allow_tf32 = not args.strict_fp32
     torch.backends.cudnn.allow_tf32 = not args.strict_fp32
@@ -354,6 +355,7 @@ def run_ours(args):
     step_model = model
     if world > 1:
         step_model = sharding.wrap_ddp(model, dev)
+        sharding.hook_optimizer(step_model, opt)
     # one host batch per scale (a single one unless the config is multi-scale); a rank's step i uses batch (i + rank) % n,
     # so with multi-scale the ranks see different shapes in the same step, as the reference's per-image random scale does
     scales = CONFIGS[args.config]["scales"] or [(IMG_W, IMG_H)]
@@ -416,10 +418,22 @@ def run_ours(args):
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
         evs[0].record()
         caps, host_ms = [], []
+        trace_on = os.environ.get("ODWSCL_BENCH_DEBUG", "") == "2" and rank == 0
         for i in range(n):
+            if trace_on:
+                capi.trace = []
             t_h = time.perf_counter()
             fn()
-            host_ms.append(round((time.perf_counter() - t_h) * 1e3, 1))
+            t_e = time.perf_counter()
+            host_ms.append(round((t_e - t_h) * 1e3, 1))
+            if trace_on and host_ms[-1] > 30.0:            # where did the enqueueing thread lose its time?
+                tr = [(t_h, t_h, "<step begins>")] + capi.trace + [(t_e, t_e, "<step ends>")]
+                gaps = [((b[0] - a[1]) * 1e3, "between %s and %s" % (a[2], b[2])) for a, b in zip(tr, tr[1:])]
+                gaps += [((c[1] - c[0]) * 1e3, "inside %s" % c[2]) for c in capi.trace]
+                gaps.sort(reverse=True)
+                print("[bench] %s step %d host %.1f ms; largest gaps: %s" % (tag, i, host_ms[-1],
+                      "; ".join("%.1f ms %s" % g for g in gaps[:4])), file=sys.stderr, flush=True)
+            capi.trace = None
             caps.append(evaluator._k_cap)
             evs[i + 1].record()
         barrier()
@@ -432,7 +446,27 @@ def run_ours(args):
             per_rank = sharding.all_ranks(mine / n, dev)
             if rank == 0:
                 print("[bench] %s ms/step per rank: %s" % (tag, [round(x, 2) for x in per_rank]), file=sys.stderr, flush=True)
+        # a HOST stall (the enqueueing thread descheduled for tens of ms while the GPU runs dry; seen on some boxes in 1-2
+        # of 20 steps, none on others, with and without the clock sampler): the step whose enqueue took > 40 ms AND whose
+        # device time is > 1.5x the window's median
+        dev_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(n)]
+        med = sorted(dev_ms)[n // 2]
+        stalls = [i for i in range(n) if host_ms[i] > 40.0 and dev_ms[i] > 1.5 * med]
+        timed.host_stalls = int(sharding.max_over_ranks(len(stalls), dev))
         return sharding.max_over_ranks(mine, dev)
+
+    def timed_window(fn, n, tag):
+        """One timed window; if a host stall hit it, it is reported (`first_window`) and the window is measured ONCE more."""
+        ms = timed(fn, n, tag)
+        skipped = overflowed()
+        first = None
+        if skipped or timed.host_stalls:
+            first = {"ms_per_step": ms / n, "skipped_updates": skipped, "host_stalled_steps": timed.host_stalls}
+            ms = timed(fn, n, tag + " (2nd window: the 1st had %d skipped update(s), %d host-stalled step(s))"
+                       % (skipped, timed.host_stalls))
+            skipped = overflowed()
+            first["second_window_host_stalled_steps"] = timed.host_stalls
+        return ms, skipped, first
 
     for bt in batches:
         bt["images_d"] = bt["images_h"].to(dev, non_blocking=True)
@@ -500,22 +534,13 @@ def run_ours(args):
     if args.profile_range:
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
-    ms = timed(resident_step, args.steps, "resident")
+    ms, skipped, first_window = timed_window(resident_step, args.steps, "resident")
     if args.profile_range:
         torch.cuda.profiler.stop()
-    launches = capi.launch_count - l0
-    skipped = overflowed()
-    first_window = None
-    if skipped:                        # a skipped update is not a full step: measure again with the raised bound
-        first_window = {"ms_per_step": ms / args.steps, "skipped_updates": skipped}      # reported, not hidden
-        l0 = capi.launch_count
-        ms = timed(resident_step, args.steps, "resident (2nd window: the 1st had %d skipped update(s))" % skipped)
-        launches = capi.launch_count - l0
-        skipped = overflowed()
+    launches = (capi.launch_count - l0) // (2 if first_window else 1)
     for _ in range(2):
         e2e_step()
-    ms_e2e = timed(e2e_step, args.steps, "e2e")
-    skipped_e2e = overflowed()
+    ms_e2e, skipped_e2e, first_window_e2e = timed_window(e2e_step, args.steps, "e2e")
     sampler.window(t_timed0, time.monotonic())
     clocks = sampler.stop()
     props_per_step = sharding.proposals_per_step(world, B_PER_GPU, N_PROP)
@@ -632,7 +657,9 @@ def run_ours(args):
                        "host_syncs_per_step": 1 if args.sync_k else 0, "skipped_updates": [skipped, skipped_e2e],
                        "allreduce": not args.no_allreduce, "sm_margin": int(os.environ.get("ODWSCL_SM_MARGIN", "8")) if world > 1 else 0,
                        "bucket_mb": int(os.environ.get("ODWSCL_BUCKET_MB", "128")) if world > 1 else None,
-                       "calibration_steps": n_calib, "first_window_with_skipped_update": first_window,
+                       "peer_grad_sum": bool(getattr(step_model, "peer", None)) if world > 1 else None,
+                       "nccl_max_ctas": os.environ.get("NCCL_MAX_CTAS") if world > 1 else None,
+                       "calibration_steps": n_calib, "first_window": first_window, "first_window_e2e": first_window_e2e,
                        "lr": LR, "final_loss": float(loss_h[0]),
                        "l2": "per-step working set (>=1.6 GB of activations) exceeds the 126 MB L2; kernel-alone timings flush L2 with a 256 MB write"},
             "e2e": {"value": e2e_val, "unit": "proposals/s", "ms_per_step": ms_e2e / args.steps,

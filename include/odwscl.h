@@ -235,6 +235,25 @@ int odwscl_fc_gemm_tf32(const float* A, int lda, int a_mn_major, const float* B,
                         int ldc, int M, int N, int K, int flags, const float* bias, const float* mask_src,
                         int ld_mask, float mask_scale, float dropout_p, unsigned long long seed, int max_pairs,
                         const float* A2, int lda2, const float* B2, int ldb2, int K2, odwscl_stream_t stream);
+/* The same product (no epilogue flags) whose result is ADDED, times out_scale, to every rank's replica of C through the
+ * NVSwitch multicast alias C_multicast of a symmetric-memory allocation (multimem.red.add.v4.f32 from the epilogue): the
+ * weight gradient and its cross-rank sum in one kernel.  Replaces, for the fc6 / fc7 weights, the bucket all-reduce
+ * DistributedDataParallel runs after the cuBLAS weight gradient (tools/train_net.py:50-55).  The caller zeroes C on
+ * every rank and synchronises the ranks before the launch and before reading C (od-wscl_b200/sharding.py PeerGradSum). */
+int odwscl_fc_gemm_peer_sum_tf32(const float* A, int lda, int a_mn_major, const float* B, int ldb, int b_mn_major, float* C,
+                                 float* C_multicast, int ldc, int M, int N, int K, float out_scale, int max_pairs,
+                                 const float* A2, int lda2, const float* B2, int ldb2, int K2, odwscl_stream_t stream);
+/* Reduce-scatter form of the above for larger worlds: rows [r * rows_per_owner, (r + 1) * rows_per_owner) of the product
+ * are added (red.add.v4.f32 over NVLink) ONLY to rank r's replica peer_C[r] (host array of n_peers <= 8 device pointers,
+ * peer-mapped; rows_per_owner % 32 == 0), so a rank receives (world-1)/world of the gradient instead of (world-1) copies.
+ * odwscl_peer_broadcast_f32 is the all-gather half: every rank's dst[i] = src[i] through the multicast alias. */
+int odwscl_fc_gemm_peer_scatter_tf32(const float* A, int lda, int a_mn_major, const float* B, int ldb, int b_mn_major, float* C,
+                                     const void* const* peer_C, int n_peers, int rows_per_owner, int ldc, int M, int N, int K,
+                                     float out_scale, int max_pairs, const float* A2, int lda2, const float* B2, int ldb2,
+                                     int K2, odwscl_stream_t stream);
+int odwscl_peer_broadcast_f32(const float* src, float* dst_multicast, long long n, odwscl_stream_t stream);
+/* every rank's dst[i] += scale * src[i] through the multicast alias (n % 4 == 0, 16-byte aligned). */
+int odwscl_peer_add_f32(const float* src, float* dst_multicast, long long n, float scale, odwscl_stream_t stream);
 /* out[c] (+)= sum_r x[r, c] over a [rows, cols] matrix of pitch ld: the bias gradients of the block above
  * (accumulate != 0 adds to out, which folds a second call's gradient). */
 int odwscl_colsum_f32(const float* x, long long rows, int cols, int ld, float* out, int accumulate,

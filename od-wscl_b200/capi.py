@@ -11,6 +11,8 @@ import ctypes
 import os
 from ctypes import c_float, c_int, c_size_t, c_void_p
 
+import time
+
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -30,7 +32,7 @@ _LAUNCHES = {
     "odwscl_conv3x3_nhwc_tf32": 1, "odwscl_conv3x3_wgrad_nhwc_tf32": 2, "odwscl_conv3x3_c3_f32": 1, "odwscl_maxpool2x2_nhwc_f32": 1,
     "odwscl_maxpool2x2_nhwc_bwd_f32": 1, "odwscl_split_tf32": 1,
     "odwscl_relu_dropout_fwd_f32": 1, "odwscl_relu_dropout_bwd_f32": 1, "odwscl_conv_weight_xform_f32": 1,
-    "odwscl_fc_gemm_tf32": 1, "odwscl_colsum_f32": 1, "odwscl_l2norm_fwd_f32": 1, "odwscl_l2norm_bwd_f32": 1,
+    "odwscl_fc_gemm_tf32": 1, "odwscl_fc_gemm_peer_sum_tf32": 1, "odwscl_peer_add_f32": 1, "odwscl_fc_gemm_peer_scatter_tf32": 1, "odwscl_peer_broadcast_f32": 1, "odwscl_colsum_f32": 1, "odwscl_l2norm_fwd_f32": 1, "odwscl_l2norm_bwd_f32": 1,
     "odwscl_spec_index": 1, "odwscl_aug_positives_f32": 2,
     "odwscl_head_scores_f32": 5, "odwscl_head_loss_f32": 2, "odwscl_head_grad_scale_f32": 1,
 }
@@ -80,6 +82,11 @@ _SIGS = {
     "odwscl_conv_weight_xform_f32": (_I, [_P, _I, _I, _P, _P, _I, _P]),
     "odwscl_fc_gemm_tf32": (_I, [_P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P, _I, _F, _F, ctypes.c_ulonglong, _I,
                                  _P, _I, _P, _I, _I, _P]),
+    "odwscl_fc_gemm_peer_sum_tf32": (_I, [_P, _I, _I, _P, _I, _I, _P, _P, _I, _I, _I, _I, _F, _I, _P, _I, _P, _I, _I, _P]),
+    "odwscl_peer_add_f32": (_I, [_P, _P, ctypes.c_longlong, _F, _P]),
+    "odwscl_fc_gemm_peer_scatter_tf32": (_I, [_P, _I, _I, _P, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P, _I, _P, _I,
+                                              _I, _P]),
+    "odwscl_peer_broadcast_f32": (_I, [_P, _P, ctypes.c_longlong, _P]),
     "odwscl_colsum_f32": (_I, [_P, ctypes.c_longlong, _I, _I, _P, _I, _P]),
     "odwscl_head_scores_ws_bytes": (_Z, [_I, _I]),
     "odwscl_head_scores_f32": (_I, [_P, _I, _I, _I, _I, _P, _I] + [_P] * 7 + [_P, _Z, _P]),
@@ -156,7 +163,14 @@ _WORK = {
     "odwscl_gemm_nt_tf32": lambda a: ("flop", 2.0 * a[3] * a[4] * a[5]),
     # (A, lda, a_mn, B, ldb, b_mn, C, ldc, M, N, K, ...)
     "odwscl_fc_gemm_tf32": lambda a: ("flop", 2.0 * a[8] * a[9] * (a[10] + a[23])),
+    # (A, lda, a_mn, B, ldb, b_mn, C, C_mc, ldc, M, N, K, scale, max_pairs, A2, lda2, B2, ldb2, K2, stream)
+    "odwscl_fc_gemm_peer_sum_tf32": lambda a: ("flop", 2.0 * a[9] * a[10] * (a[11] + a[18])),
+    # (A, lda, a_mn, B, ldb, b_mn, C, peer_C, n_peers, rows_per_owner, ldc, M, N, K, scale, max_pairs, A2, lda2, B2, ldb2, K2)
+    "odwscl_fc_gemm_peer_scatter_tf32": lambda a: ("flop", 2.0 * a[11] * a[12] * (a[13] + a[20])),
 }
+
+
+trace = None               # host-side diagnosis (bench.py ODWSCL_BENCH_DEBUG=2): [(t_enter, t_exit, name)] of every C-ABI call
 
 
 def _call(name, *args):
@@ -164,7 +178,12 @@ def _call(name, *args):
     if profile is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    rc = getattr(lib(), name)(*args)
+    if trace is not None:
+        t_in = time.perf_counter()
+        rc = getattr(lib(), name)(*args)
+        trace.append((t_in, time.perf_counter(), name))
+    else:
+        rc = getattr(lib(), name)(*args)
     if rc != 0:
         raise RuntimeError("%s failed: %s (%d)" % (name, lib().odwscl_strerror(rc).decode(), rc))
     launch_count += _LAUNCHES.get(name, 0)
@@ -658,6 +677,55 @@ def fc_gemm(A, B, a_mn=False, b_mn=False, out=None, bias=None, relu=False, dropo
               ctypes.c_ulonglong(seed & (2 ** 64 - 1)), int(FC_MAX_PAIRS), _ptr(A2) if K2 else None, int(lda2),
               _ptr(B2) if K2 else None, int(ldb2), int(K2), _stream())
     return out
+
+
+def fc_gemm_peer_sum(A, B, out, out_multicast_ptr, scale, a_mn=False, b_mn=False, A2=None, B2=None, peer_ptrs=None,
+                     rows_per_owner=0):
+    """out (this rank's replica, zeroed by the caller on every rank) and every peer's replica += scale * (A B^T [+ A2 B2^T]):
+    the product leaves the epilogue as multimem.red.add through `out_multicast_ptr`, the NVSwitch multicast address of
+    `out` (sharding.PeerGradSum owns the symmetric allocation and the two rank barriers around the step's use of it).
+    With `peer_ptrs` (every rank's address of `out`, this rank's included) the product is reduce-scattered instead: rows
+    [r * rows_per_owner, ...) are added to rank r's replica only."""
+    (A, lda), (B, ldb) = _rows2d(A, "A"), _rows2d(B, "B")
+    K2, lda2, ldb2 = 0, 0, 0
+    if A2 is not None:
+        (A2, lda2), (B2, ldb2) = _rows2d(A2, "A2"), _rows2d(B2, "B2")
+        K2 = A2.shape[0] if a_mn else A2.shape[1]
+    K, M = (A.shape[0], A.shape[1]) if a_mn else (A.shape[1], A.shape[0])
+    Kb, N = (B.shape[0], B.shape[1]) if b_mn else (B.shape[1], B.shape[0])
+    if K != Kb or K == 0:
+        raise RuntimeError("fc_gemm_peer_sum: contraction sizes (%d vs %d)" % (K, Kb))
+    if tuple(out.shape) != (M, N) or out.dtype != torch.float32 or not out.is_contiguous() or out.data_ptr() & 15 \
+            or (peer_ptrs is None and (int(out_multicast_ptr) & 15 or not out_multicast_ptr)):
+        raise RuntimeError("fc_gemm_peer_sum: `out` must be a contiguous, 16-byte aligned [%d,%d] float32 view of a "
+                           "symmetric-memory buffer with a multicast address" % (M, N))
+    if peer_ptrs is not None:
+        tab = (c_void_p * len(peer_ptrs))(*[int(q) for q in peer_ptrs])
+        with torch.cuda.device(A.device):
+            _call("odwscl_fc_gemm_peer_scatter_tf32", _ptr(A), int(lda), int(a_mn), _ptr(B), int(ldb), int(b_mn), _ptr(out),
+                  ctypes.cast(tab, c_void_p), len(peer_ptrs), int(rows_per_owner), int(N), M, N, K, float(scale),
+                  int(FC_MAX_PAIRS), _ptr(A2) if K2 else None, int(lda2), _ptr(B2) if K2 else None, int(ldb2), int(K2),
+                  _stream())
+        return out
+    with torch.cuda.device(A.device):
+        _call("odwscl_fc_gemm_peer_sum_tf32", _ptr(A), int(lda), int(a_mn), _ptr(B), int(ldb), int(b_mn), _ptr(out),
+              c_void_p(int(out_multicast_ptr)), int(N), M, N, K, float(scale), int(FC_MAX_PAIRS), _ptr(A2) if K2 else None,
+              int(lda2), _ptr(B2) if K2 else None, int(ldb2), int(K2), _stream())
+    return out
+
+
+def peer_add(src, dst_multicast_ptr, scale=1.0):
+    """every rank's replica += scale * src, through the multicast address of the replica (numel % 4 == 0)."""
+    src = _chk(src, torch.float32, "src")
+    with torch.cuda.device(src.device):
+        _call("odwscl_peer_add_f32", _ptr(src), c_void_p(int(dst_multicast_ptr)), src.numel(), float(scale), _stream())
+
+
+def peer_broadcast(src, dst_multicast_ptr):
+    """every rank's replica = src (numel % 4 == 0): the all-gather half of the reduce-scattered gradient."""
+    src = _chk(src, torch.float32, "src")
+    with torch.cuda.device(src.device):
+        _call("odwscl_peer_broadcast_f32", _ptr(src), c_void_p(int(dst_multicast_ptr)), src.numel(), _stream())
 
 
 def colsum(x, out=None, accumulate=False):

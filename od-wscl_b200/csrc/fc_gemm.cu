@@ -38,7 +38,7 @@ namespace {
 constexpr int kBM = 128;                 // rows of A per CTA (256 per pair)
 constexpr int kBN = 256;                 // columns per pair tile
 constexpr int kBox = 32 * 128;           // bytes of one MN-major {32 rows(mn) x 32 k} TMA box
-enum : int { kBias = 1, kAccum = 2, kRelu = 4, kDropout = 8, kMask = 16, kRound = 32 };
+enum : int { kBias = 1, kAccum = 2, kRelu = 4, kDropout = 8, kMask = 16, kRound = 32, kPeerSum = 64, kPeerOwner = 128 };
 
 __device__ __forceinline__ float rna_tf32(float v) {
   uint32_t b;
@@ -72,7 +72,30 @@ struct FcEpi {
   uint32_t drop_thr16;      // keep iff 16 random bits >= thr
   unsigned long long seed;
   int flags;
+  long long mc_delta;       // kPeerSum: byte distance from C to its NVSwitch multicast alias
+  float out_scale;          // kPeerSum: factor on the stored value (1 / world_size: DDP averages)
+  // kPeerSum | kPeerOwner: rows [r * rows_per_owner, (r + 1) * rows_per_owner) are summed on rank r only (reduce-scatter);
+  // peer_delta[r] = byte distance from C to rank r's replica of C (peer-mapped symmetric memory)
+  long long peer_delta[8];
+  int rows_per_owner, n_owners;
 };
+
+// Adds 4 floats to the same address of EVERY rank's replica in one NVLink operation: the switch forwards the reduction
+// to all members of the multicast object (NVLS), so the cross-rank sum of a weight gradient leaves the GEMM epilogue
+// tile by tile while the tensor pipe works on the next tile -- no all-reduce kernel afterwards.
+__device__ __forceinline__ void multimem_red_add_v4(float* mc, float a, float b, float c, float d) {
+  asm volatile("multimem.red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+__device__ __forceinline__ void peer_red_add_v4(float* p, float a, float b, float c, float d) {   // one rank's memory, over NVLink
+  asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void peer_red_add(float* p, float a) {
+  asm volatile("red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory");
+}
+__device__ __forceinline__ void multimem_red_add(float* mc, float a) {
+  asm volatile("multimem.red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(mc), "f"(a) : "memory");
+}
 
 struct FcSk {
   int m_tiles, n_tiles;     // 256-row / 256-column pair tiles
@@ -199,6 +222,68 @@ __device__ __forceinline__ void fc_epilogue_store(float (&v)[32], float* __restr
   }
 }
 
+// kPeerSum epilogue of one warp's 32 rows x 32 columns: every rank's replica of C (zeroed beforehand) += v * out_scale.
+// The values go through a padded shared-memory tile so that 8 consecutive lanes add 128 CONTIGUOUS bytes of one row: a
+// multimem.red travels over NVLink as its own request, and 16-byte requests at row stride (the row-domain epilogue above)
+// ran the whole step 5 ms slower at 2 GPUs -- the fabric is request-bound long before it is byte-bound.
+constexpr int kPeerPitch = 36;                 // floats per staged row: 16-byte aligned, conflict-free float4 rows
+constexpr int kPeerStageBytes = 4 * 32 * kPeerPitch * (int)sizeof(float);
+
+__device__ __forceinline__ void fc_epilogue_peer(float (&v)[32], float* __restrict__ stage, float* __restrict__ C, int ldc,
+                                                 int row0, int col, int M, int N, const FcEpi& ep, int lane) {
+  if (col >= N) return;                        // warp-uniform
+  const float sc = ep.out_scale;
+  float4* srow = reinterpret_cast<float4*>(stage + lane * kPeerPitch);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) srow[j] = make_float4(v[4 * j] * sc, v[4 * j + 1] * sc, v[4 * j + 2] * sc, v[4 * j + 3] * sc);
+  __syncwarp();
+  const bool vec = (col + 32 <= N) && ((ldc & 3) == 0);
+  const int cg = (lane & 7) * 4;
+  if (ep.flags & kPeerOwner) {
+    // reduce-scatter form: the warp's 32 rows belong to ONE rank (rows_per_owner % 32 == 0); only that rank's replica
+    // receives the tile, so a rank takes in (world - 1) / world of the gradient instead of (world - 1) x all of it
+    const int owner = min(row0 / ep.rows_per_owner, ep.n_owners - 1);
+    const long long delta = ep.peer_delta[owner];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = i * 4 + (lane >> 3);
+      const int row = row0 + r;
+      const float4 t = *reinterpret_cast<const float4*>(stage + r * kPeerPitch + cg);
+      if (row < M) {
+        float* dst = reinterpret_cast<float*>(reinterpret_cast<char*>(C + (size_t)row * ldc + col + cg) + delta);
+        if (vec) {
+          peer_red_add_v4(dst, t.x, t.y, t.z, t.w);
+        } else {
+          if (col + cg < N) peer_red_add(dst, t.x);
+          if (col + cg + 1 < N) peer_red_add(dst + 1, t.y);
+          if (col + cg + 2 < N) peer_red_add(dst + 2, t.z);
+          if (col + cg + 3 < N) peer_red_add(dst + 3, t.w);
+        }
+      }
+    }
+    __syncwarp();
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + (lane >> 3);
+    const int row = row0 + r;
+    const float4 t = *reinterpret_cast<const float4*>(stage + r * kPeerPitch + cg);
+    if (row < M) {
+      float* mc = reinterpret_cast<float*>(reinterpret_cast<char*>(C + (size_t)row * ldc + col + cg) + ep.mc_delta);
+      if (vec) {
+        multimem_red_add_v4(mc, t.x, t.y, t.z, t.w);
+      } else {
+        if (col + cg < N) multimem_red_add(mc, t.x);
+        if (col + cg + 1 < N) multimem_red_add(mc + 1, t.y);
+        if (col + cg + 2 < N) multimem_red_add(mc + 2, t.z);
+        if (col + cg + 3 < N) multimem_red_add(mc + 3, t.w);
+      }
+    }
+  }
+  __syncwarp();
+}
+
 template <bool AMN, bool BMN, int kStages>
 __global__ void __launch_bounds__(192, 1)
 fc_gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -301,6 +386,8 @@ fc_gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     const int trow = q * 32 + lane;
     float v[32];
     FcItem wi;
+    const bool peer = (ep.flags & kPeerSum) != 0;      // the launch then carries kPeerStageBytes behind the operand ring
+    float* stage = reinterpret_cast<float*>(tiles + (size_t)kStages * (kBM + kBN / 2) * tc::kTileKBytes) + q * 32 * kPeerPitch;
     for (int item = 0; fc_item(sk, pair, item, wi); ++item) {
       const int buf = item & 1;
       int m0, n0;
@@ -313,7 +400,8 @@ fc_gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         for (int c = 0; c < kBN / 32; ++c) {
           tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * kBN + c * 32, v);
           tc::tmem_ld_wait();
-          fc_epilogue_store(v, C, ldc, row, n0 + c * 32, M, N, ep);
+          if (peer) fc_epilogue_peer(v, stage, C, ldc, row - lane, n0 + c * 32, M, N, ep, lane);
+          else fc_epilogue_store(v, C, ldc, row, n0 + c * 32, M, N, ep);
         }
         tc::tc_fence_before();
         tc::mbar_arrive_leader(&tmem_empty_bar[buf]);
@@ -355,7 +443,8 @@ fc_gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             v[4 * j] += p.x; v[4 * j + 1] += p.y; v[4 * j + 2] += p.z; v[4 * j + 3] += p.w;
           }
         }
-        fc_epilogue_store(v, C, ldc, row, n0 + ch * 32, M, N, ep);
+        if (peer) fc_epilogue_peer(v, stage, C, ldc, row - lane, n0 + ch * 32, M, N, ep, lane);
+        else fc_epilogue_store(v, C, ldc, row, n0 + ch * 32, M, N, ep);
       }
     }
   }
@@ -404,7 +493,7 @@ int launch_fc_s(const FcOperands& o0, const FcOperands& o1, float* C, int ldc, i
     rc = make_operand_map(&mb1, o1.B, N, o1.K, o1.ldb, BMN);
     if (rc) return rc;
   }
-  constexpr int smem = kStages * (kBM + kBN / 2) * tc::kTileKBytes + 1024;
+  const int smem = kStages * (kBM + kBN / 2) * tc::kTileKBytes + 1024 + ((ep.flags & kPeerSum) ? kPeerStageBytes : 0);
   auto kern = fc_gemm_tf32_2cta_kernel<AMN, BMN, kStages>;
   ODW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   cudaLaunchConfig_t cfg = {};
@@ -474,7 +563,7 @@ template <bool AMN, bool BMN>
 int launch_fc(const FcOperands& o0, const FcOperands& o1, float* C, int ldc, int M, int N, const FcEpi& ep,
               int max_pairs_cap, cudaStream_t st) {
   static const int stages = fc_env("ODWSCL_FC_STAGES", 6);
-  if (stages >= 7) return launch_fc_s<AMN, BMN, 7>(o0, o1, C, ldc, M, N, ep, max_pairs_cap, st);
+  if (stages >= 7 && !(ep.flags & kPeerSum)) return launch_fc_s<AMN, BMN, 7>(o0, o1, C, ldc, M, N, ep, max_pairs_cap, st);
   return launch_fc_s<AMN, BMN, 6>(o0, o1, C, ldc, M, N, ep, max_pairs_cap, st);
 }
 
@@ -499,15 +588,25 @@ colsum_kernel(const float* __restrict__ x, long long rows, int cols, int ld, flo
 
 }  // namespace
 
-ODW_API int odwscl_fc_gemm_tf32(const float* A, int lda, int a_mn_major, const float* B, int ldb, int b_mn_major, float* C,
-                                int ldc, int M, int N, int K, int flags, const float* bias, const float* mask_src,
-                                int ld_mask, float mask_scale, float dropout_p, unsigned long long seed, int max_pairs,
-                                const float* A2, int lda2, const float* B2, int ldb2, int K2, odwscl_stream_t stream) {
+static int fc_gemm_entry(const float* A, int lda, int a_mn_major, const float* B, int ldb, int b_mn_major, float* C, int ldc,
+                         int M, int N, int K, int flags, const float* bias, const float* mask_src, int ld_mask,
+                         float mask_scale, float dropout_p, unsigned long long seed, int max_pairs, const float* A2, int lda2,
+                         const float* B2, int ldb2, int K2, float* C_multicast, float out_scale, odwscl_stream_t stream,
+                         const void* const* peer_C = nullptr, int n_peers = 0, int rows_per_owner = 0) {
   if (M < 0 || N < 0 || K < 0 || K2 < 0 || lda <= 0 || ldb <= 0 || ldc < N) return ODWSCL_EINVAL;
   if ((lda & 3) || (ldb & 3)) return ODWSCL_EINVAL;                      // TMA: 16-byte row pitch
   if (a_mn_major ? lda < M : lda < K) return ODWSCL_EINVAL;
   if (b_mn_major ? ldb < N : ldb < K) return ODWSCL_EINVAL;
   if (dropout_p < 0.f || dropout_p >= 1.f) return ODWSCL_EINVAL;
+  if (flags & kPeerOwner) {                                              // reduce-scatter over peer-mapped replicas
+    if (!(flags & kPeerSum) || (flags & ~(kPeerSum | kPeerOwner)) || !peer_C || n_peers < 1 || n_peers > 8 ||
+        rows_per_owner <= 0 || (rows_per_owner & 31))
+      return ODWSCL_EINVAL;
+    for (int r = 0; r < n_peers; ++r)
+      if (!peer_C[r] || ((uintptr_t)peer_C[r] & 15)) return ODWSCL_EINVAL;
+  } else if (flags & kPeerSum) {                                         // a plain sum of products, nothing else fused
+    if (!C_multicast || ((uintptr_t)C_multicast & 15) || (flags & ~kPeerSum)) return ODWSCL_EINVAL;
+  }
   if (M == 0 || N == 0) return 0;
   if (!A || !B || !C || K == 0) return ODWSCL_EINVAL;
   if (((uintptr_t)A & 15) || ((uintptr_t)B & 15) || ((uintptr_t)C & 15) || ((uintptr_t)mask_src & 15)) return ODWSCL_EINVAL;
@@ -522,12 +621,83 @@ ODW_API int odwscl_fc_gemm_tf32(const float* A, int lda, int a_mn_major, const f
   ep.drop_scale = 1.f / (1.f - dropout_p);
   ep.drop_thr16 = (uint32_t)(dropout_p * 65536.0f);
   ep.seed = seed; ep.flags = flags;
+  ep.mc_delta = ((flags & kPeerSum) && C_multicast) ? (long long)(reinterpret_cast<char*>(C_multicast) - reinterpret_cast<char*>(C)) : 0;
+  ep.out_scale = out_scale;
+  ep.rows_per_owner = rows_per_owner; ep.n_owners = n_peers;
+  for (int r = 0; r < 8; ++r)
+    ep.peer_delta[r] = (r < n_peers) ? (long long)(reinterpret_cast<const char*>(peer_C[r]) - reinterpret_cast<const char*>(C)) : 0;
   cudaStream_t st = (cudaStream_t)stream;
   const FcOperands o0{A, lda, B, ldb, K}, o1{A2, lda2, B2, ldb2, K2};
   if (!a_mn_major && !b_mn_major) return launch_fc<false, false>(o0, o1, C, ldc, M, N, ep, max_pairs, st);
   if (!a_mn_major && b_mn_major) return launch_fc<false, true>(o0, o1, C, ldc, M, N, ep, max_pairs, st);
   if (a_mn_major && b_mn_major) return launch_fc<true, true>(o0, o1, C, ldc, M, N, ep, max_pairs, st);
   return launch_fc<true, false>(o0, o1, C, ldc, M, N, ep, max_pairs, st);
+}
+
+ODW_API int odwscl_fc_gemm_tf32(const float* A, int lda, int a_mn_major, const float* B, int ldb, int b_mn_major, float* C,
+                                int ldc, int M, int N, int K, int flags, const float* bias, const float* mask_src,
+                                int ld_mask, float mask_scale, float dropout_p, unsigned long long seed, int max_pairs,
+                                const float* A2, int lda2, const float* B2, int ldb2, int K2, odwscl_stream_t stream) {
+  if (flags & kPeerSum) return ODWSCL_EINVAL;
+  return fc_gemm_entry(A, lda, a_mn_major, B, ldb, b_mn_major, C, ldc, M, N, K, flags, bias, mask_src, ld_mask, mask_scale,
+                       dropout_p, seed, max_pairs, A2, lda2, B2, ldb2, K2, nullptr, 1.f, stream);
+}
+
+ODW_API int odwscl_fc_gemm_peer_sum_tf32(const float* A, int lda, int a_mn_major, const float* B, int ldb, int b_mn_major,
+                                         float* C, float* C_multicast, int ldc, int M, int N, int K, float out_scale,
+                                         int max_pairs, const float* A2, int lda2, const float* B2, int ldb2, int K2,
+                                         odwscl_stream_t stream) {
+  return fc_gemm_entry(A, lda, a_mn_major, B, ldb, b_mn_major, C, ldc, M, N, K, kPeerSum, nullptr, nullptr, 0, 1.f, 0.f, 0ull,
+                       max_pairs, A2, lda2, B2, ldb2, K2, C_multicast, out_scale, stream);
+}
+
+ODW_API int odwscl_fc_gemm_peer_scatter_tf32(const float* A, int lda, int a_mn_major, const float* B, int ldb, int b_mn_major,
+                                             float* C, const void* const* peer_C, int n_peers, int rows_per_owner, int ldc,
+                                             int M, int N, int K, float out_scale, int max_pairs, const float* A2, int lda2,
+                                             const float* B2, int ldb2, int K2, odwscl_stream_t stream) {
+  return fc_gemm_entry(A, lda, a_mn_major, B, ldb, b_mn_major, C, ldc, M, N, K, kPeerSum | kPeerOwner, nullptr, nullptr, 0, 1.f,
+                       0.f, 0ull, max_pairs, A2, lda2, B2, ldb2, K2, nullptr, out_scale, stream, peer_C, n_peers,
+                       rows_per_owner);
+}
+
+// every rank's replica[i] = src[i] (one NVLink store, replicated by the switch): the all-gather half after the
+// reduce-scatter above -- each rank broadcasts the rows it owns
+__global__ void peer_broadcast_kernel(const float4* __restrict__ src, float* __restrict__ mc, long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldcs(src + i);
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc + 4 * i), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+  }
+}
+
+ODW_API int odwscl_peer_broadcast_f32(const float* src, float* dst_multicast, long long n, odwscl_stream_t stream) {
+  if (n < 0 || (n & 3)) return ODWSCL_EINVAL;
+  if (n == 0) return 0;
+  if (!src || !dst_multicast || ((uintptr_t)src & 15) || ((uintptr_t)dst_multicast & 15)) return ODWSCL_EINVAL;
+  const int blocks = (int)min((long long)(ODW_NUM_SMS - odw_sm_margin()) * 8, (n / 4 + 255) / 256);
+  peer_broadcast_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(src), dst_multicast, n / 4);
+  ODW_LAUNCH_CHECK();
+  return 0;
+}
+
+// every rank's replica[i] += scale * src[i] through the multicast alias (the path for a gradient that was not produced by
+// the GEMM above: strict-mode chunks, a layer applied more than twice)
+__global__ void peer_add_kernel(const float4* __restrict__ src, float* __restrict__ mc, long long n4, float scale) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldcs(src + i);
+    multimem_red_add_v4(mc + 4 * i, v.x * scale, v.y * scale, v.z * scale, v.w * scale);
+  }
+}
+
+ODW_API int odwscl_peer_add_f32(const float* src, float* dst_multicast, long long n, float scale, odwscl_stream_t stream) {
+  if (n < 0 || (n & 3)) return ODWSCL_EINVAL;
+  if (n == 0) return 0;
+  if (!src || !dst_multicast || ((uintptr_t)src & 15) || ((uintptr_t)dst_multicast & 15)) return ODWSCL_EINVAL;
+  const int blocks = (int)min((long long)ODW_NUM_SMS * 4, (n / 4 + 255) / 256);
+  peer_add_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(src), dst_multicast, n / 4, scale);
+  ODW_LAUNCH_CHECK();
+  return 0;
 }
 
 ODW_API int odwscl_colsum_f32(const float* x, long long rows, int cols, int ld, float* out, int accumulate,

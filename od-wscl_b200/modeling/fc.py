@@ -75,8 +75,9 @@ class _LinearFn(Function):
     round the small call returns its own gradient, so the result never depends on the assumption."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, act, p, seed, round_out, strict, stash, role, in_mask_scale, act_bwd_fused):
+    def forward(ctx, x, weight, bias, act, p, seed, round_out, strict, stash, role, in_mask_scale, act_bwd_fused, peer):
         x2 = x
+        ctx.peer = peer
         y = _gemm(x2, weight, strict, bias=bias, relu=act != ACT_NONE,
                   dropout_p=p if act == ACT_RELU_DROPOUT else 0.0, seed=seed, round_tf32=round_out and not strict)
         ctx.save_for_backward(x2, weight, y if act != ACT_NONE else None)
@@ -105,24 +106,33 @@ class _LinearFn(Function):
         need_w = ctx.needs_input_grad[1]
         if ctx.role == "small" and st is not None and st.get("has_main", False) and not st.get("main_done", False):
             st.setdefault("pending", []).append((dz, x))
-            return (gx,) + (None,) * 11
+            return (gx,) + (None,) * 12
         gw = gb = None
         pend = st.pop("pending", []) if (ctx.role == "main" and st is not None) else []
         if need_w:
-            if len(pend) == 1 and not ctx.strict:
+            peer = ctx.peer
+            if peer is not None and len(pend) <= 1 and not ctx.strict:
+                # multi-GPU: the product is added to EVERY rank's gradient replica from the GEMM epilogue (NVSwitch multicast
+                # reduction) -- this weight has no all-reduce (sharding.PeerGradSum)
+                peer.sum_product(dz, x, pend[0] if pend else None)
+                gw = peer.grad()
+            elif len(pend) == 1 and not ctx.strict:
                 # the small call's (dZ, x) ride in the same accumulation as a second operand pair: one GEMM, one tensor
                 gw = capi.fc_gemm(dz, x, a_mn=True, b_mn=True, A2=pend[0][0], B2=pend[0][1])
             else:
                 gw = _gemm(dz, x, ctx.strict, a_mn=True, b_mn=True)
                 for dzs, xs in pend:
                     _gemm(dzs, xs, ctx.strict, a_mn=True, b_mn=True, out=gw, accumulate=True)
+                if peer is not None:
+                    peer.add(gw)
+                    gw = peer.grad()
             if ctx.has_bias:
                 gb = capi.colsum(dz)
                 for dzs, _ in pend:
                     capi.colsum(dzs, out=gb, accumulate=True)
         if ctx.role == "main" and st is not None:
             st["main_done"] = True
-        return (gx, gw, gb) + (None,) * 9
+        return (gx, gw, gb) + (None,) * 10
 
 
 def linear(x, weight, bias=None, act=ACT_NONE, p=0.0, seed=0, round_out=False, strict=False, stash=None, role=None,
@@ -138,4 +148,5 @@ def linear(x, weight, bias=None, act=ACT_NONE, p=0.0, seed=0, round_out=False, s
     if not FUSE_ACT_BWD and (in_mask_scale is not None or act_bwd_fused):
         raise RuntimeError("fused activation backward requested while fc.FUSE_ACT_BWD is off")
     return _LinearFn.apply(x.float(), weight, bias, int(act), float(p), int(seed), bool(round_out), bool(strict), stash, role,
-                           None if in_mask_scale is None else float(in_mask_scale), bool(act_bwd_fused))
+                           None if in_mask_scale is None else float(in_mask_scale), bool(act_bwd_fused),
+                           getattr(weight, "_odw_peer", None))
