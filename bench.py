@@ -655,7 +655,7 @@ def run_ours(args):
             "config": {"workload": WORKLOAD,
                        "images_per_gpu": B_PER_GPU, "proposals_per_image": N_PROP, "parallelism": "dp%d" % world,
                        "host_syncs_per_step": 1 if args.sync_k else 0, "skipped_updates": [skipped, skipped_e2e],
-                       "allreduce": not args.no_allreduce, "sm_margin": int(os.environ.get("ODWSCL_SM_MARGIN", "8")) if world > 1 else 0,
+                       "allreduce": not args.no_allreduce, "sm_margin": sharding.plan(world)[1] if world > 1 else 0,
                        "bucket_mb": int(os.environ.get("ODWSCL_BUCKET_MB", "128")) if world > 1 else None,
                        "peer_grad_sum": bool(getattr(step_model, "peer", None)) if world > 1 else None,
                        "nccl_max_ctas": os.environ.get("NCCL_MAX_CTAS") if world > 1 else None,

@@ -35,14 +35,27 @@ def rank_seed(base, rank, images_per_rank):
     return base + rank * images_per_rank
 
 
-DEFAULT_SM_MARGIN = 8
+PEER_PUSH_ALL_MAX = 2         # largest world whose fc gradients are pushed to every replica from the GEMM epilogue
+
+
+def plan(world):
+    """(peer gradient sum on?, SMs left to NCCL during the backward) for a world size, from the round-2 measurements
+    (profiles/r02_scaling.md; ms/step at configs[1], same-box 1-GPU step 16.8-17.3):
+        2 GPUs   peer sum (push to all) + margin 8: 17.6-17.9     all-reduce + margin 16: 18.2-18.5
+        4 GPUs   peer sum (push to all) + margin 8: 18.6          all-reduce + margin 16: 18.3
+        8 GPUs   peer sum (reduce-scatter) + margin 8: 19.0       all-reduce + margin 16: 18.5-18.7     push to all: 20.8-21.3
+    ODWSCL_PEER_SUM=0|1 and ODWSCL_SM_MARGIN override."""
+    env = os.environ.get("ODWSCL_PEER_SUM", "auto")
+    peer = env == "1" or (env == "auto" and world == 2)
+    margin = int(os.environ.get("ODWSCL_SM_MARGIN", "8" if peer else "16"))
+    return peer, margin
 
 
 def configure_nccl():
     """Call before init_process_group: NCCL may use at most as many CTAs as the SMs the persistent conv / fc kernels leave
-    free during the backward (ODWSCL_SM_MARGIN), so an all-reduce kernel always finds room beside them and never holds a
-    persistent grid's last CTAs back (see wrap_ddp).  An explicit NCCL_MAX_CTAS wins."""
-    margin = int(os.environ.get("ODWSCL_SM_MARGIN", str(DEFAULT_SM_MARGIN)))
+    free during the backward, so an all-reduce kernel always finds room beside them and never holds a persistent grid's
+    last CTAs back (see wrap_ddp).  An explicit NCCL_MAX_CTAS wins."""
+    _, margin = plan(int(os.environ.get("WORLD_SIZE", "1")))
     if margin > 0:
         os.environ.setdefault("NCCL_MAX_CTAS", str(margin))
 
@@ -138,9 +151,10 @@ class PeerGradSum:
     Two forms.  world <= PEER_PUSH_ALL_MAX: every tile goes to EVERY replica (multimem.red, one NVLink operation replicated
     by the switch) and nothing else is needed -- measured at 2 GPUs: 17.6 ms/step against 18.2-18.5 with the all-reduce.
     A rank then takes in (world - 1) gradients per step, which at 8 GPUs (3.75 GB) saturates its NVLink ingress (21 ms/step
-    measured).  Larger worlds therefore reduce-scatter from the epilogue (each 32-row block of the gradient is added to its
-    owner rank only: red.add over NVLink to the peer-mapped replica) and all-gather the owned rows by multicast store in
-    before_step(): (world - 1) / world of the gradient in and out per rank."""
+    measured).  Larger worlds (only with ODWSCL_PEER_SUM=1: plan() keeps them on the all-reduce, which measured 0.3 ms
+    faster) reduce-scatter from the epilogue (each 32-row block of the gradient is added to its owner rank only: red.add
+    over NVLink to the peer-mapped replica) and all-gather the owned rows by multicast store in before_step():
+    (world - 1) / world of the gradient in and out per rank, the gather (0.6 ms at 8 GPUs) exposed."""
 
     def __init__(self, params, device, group=None):
         import torch.distributed._symmetric_memory as symm_mem
@@ -190,7 +204,6 @@ class PeerGradSum:
         self.hooked = True
 
 
-PEER_PUSH_ALL_MAX = 4         # up to this world size every tile is pushed to every replica; above: reduce-scatter + all-gather
 PEER_MIN_NUMEL = 4 << 20      # weights at least this large leave DDP's buckets (fc6 102.8 M, fc7 / Sim_Net 16.8 M each)
 
 
@@ -214,14 +227,14 @@ def wrap_ddp(model, device=None):
         # and the NEXT persistent grid no longer fits: its last CTAs -- and the split-K slices spinning on them -- wait for
         # the 411 MB fc6 bucket to finish.  Measured at 2 GPUs: steps of 37 / 67 / 131 ms among 17.8 ms ones with margin 0,
         # a flat 18.2-19.1 ms with margin 8 (profiles/r02_scaling.md).
-        margin = int(os.environ.get("ODWSCL_SM_MARGIN", str(DEFAULT_SM_MARGIN)))
+        use_peer, margin = plan(dist.get_world_size())
     else:
-        margin = 0
+        use_peer, margin = False, 0
     # 611 MB of fp32 gradients per step: large buckets (NVSwitch collectives are latency-, not link-bound) and gradients
     # stored as views of the buckets
     bucket_mb = int(os.environ.get("ODWSCL_BUCKET_MB", "128"))
     peer = None
-    if ids is not None and dist.get_world_size() > 1 and os.environ.get("ODWSCL_PEER_SUM", "1") != "0":
+    if use_peer and dist.get_world_size() > 1:
         cand = _peer_candidates(model)
         try:
             peer = PeerGradSum([p for _, p in cand], device)

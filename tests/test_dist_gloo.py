@@ -115,3 +115,42 @@ def test_sharding_rules():
     assert sorted(sum(ids, [])) == list(range(8))
     assert sharding.rank_seed(1234, 3, 2) == 1240
     assert sharding.proposals_per_step(8, 2, 2000) == 32000
+
+
+def test_multi_gpu_plan(monkeypatch):
+    """Which gradient exchange a world size gets (measured choice, profiles/r02_scaling.md) and the NCCL CTA cap that goes
+    with the SM margin; the peer-sum targets split a weight's rows into 32-row-aligned owner blocks that cover it."""
+    from odwscl_b200 import sharding
+    for k in ("ODWSCL_PEER_SUM", "ODWSCL_SM_MARGIN", "NCCL_MAX_CTAS"):
+        monkeypatch.delenv(k, raising=False)
+    assert sharding.plan(2) == (True, 8)
+    assert sharding.plan(4) == (False, 16) and sharding.plan(8) == (False, 16)
+    monkeypatch.setenv("ODWSCL_PEER_SUM", "1")
+    assert sharding.plan(8) == (True, 8)
+    monkeypatch.setenv("ODWSCL_SM_MARGIN", "4")
+    assert sharding.plan(8) == (True, 4)
+    monkeypatch.delenv("ODWSCL_PEER_SUM")
+    monkeypatch.delenv("ODWSCL_SM_MARGIN")
+    monkeypatch.setenv("WORLD_SIZE", "8")
+    sharding.configure_nccl()
+    import os
+    assert os.environ["NCCL_MAX_CTAS"] == "16"
+    monkeypatch.setenv("NCCL_MAX_CTAS", "24")              # an explicit setting wins
+    sharding.configure_nccl()
+    assert os.environ["NCCL_MAX_CTAS"] == "24"
+
+    class _Owner:
+        def __init__(self, world, rank):
+            self.world, self.rank, self.scatter, self.scale = world, rank, True, 1.0 / world
+    import torch
+    for rows in (4096, 300, 31, 128):
+        for world in (2, 3, 8):
+            p = torch.nn.Parameter(torch.zeros(rows, 8))
+            spans = [sharding._PeerTarget(_Owner(world, r), p, p.data, 0, [0] * world) for r in range(world)]
+            rpo = spans[0].rows_per_owner
+            assert rpo % 32 == 0 and rpo * world >= rows
+            covered = [r for t in spans for r in range(*t.own)]
+            assert covered == list(range(rows))             # disjoint, in order, complete
+            for t in spans:                                  # the kernel's rule: owner = min(row0 // rpo, world - 1)
+                for r in range(*t.own):
+                    assert min((r // 32 * 32) // rpo, world - 1) == t.owner.rank
