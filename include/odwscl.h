@@ -156,6 +156,18 @@ int odwscl_supcon_bwd_f32(const float* F, const float* E, int R, const int32_t* 
                           const int32_t* row_lab, const float* row_w, const int32_t* M_dev, int Mcap,
                           float inv_temp, const float* stats, const float* gscale_dev, float* dF,
                           float* dE, odwscl_stream_t stream);
+/* The same loss and gradient with both M x M contractions on the tensor cores (3xTF32 through odwscl_fc_gemm_tf32: the bank
+ * rows are gathered once as [Vh | Vh | Vl] / [Vh | Vl | Vh] so S = V V^T is ONE K = 384 GEMM; dV = H V likewise): for the
+ * banks of 8 images per rank (M = 4-6 k), where the tile kernels above grow quadratically on the FFMA pipe.  `ws`
+ * (odwscl_supcon_tc_ws_bytes(Mcap) bytes, 16-byte aligned) holds S between the forward and the backward call of a bank;
+ * `stats` as above. */
+size_t odwscl_supcon_tc_ws_bytes(int Mcap);
+int odwscl_supcon_tc_fwd_f32(const float* F, const float* E, int R, const int32_t* row_src, const int32_t* row_lab,
+                             const float* row_w, const int32_t* M_dev, int Mcap, float inv_temp, float* ws, size_t ws_bytes,
+                             float* stats, float* loss_out, odwscl_stream_t stream);
+int odwscl_supcon_tc_bwd_f32(int R, const int32_t* row_src, const int32_t* row_lab, const float* row_w, const int32_t* M_dev,
+                             int Mcap, float inv_temp, float* ws, size_t ws_bytes, const float* stats,
+                             const float* gscale_dev, float* dF, float* dE, odwscl_stream_t stream);
 
 /* ---- A13: od_layer (weak_head/pseudo_label_generator.py:135-197): per (image, branch) the
  * pseudo-GT set from `inst`, IoU+1 N x G with first-max argmax on device (no numpy round trip),

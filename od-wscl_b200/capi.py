@@ -27,7 +27,7 @@ _LAUNCHES = {
     "odwscl_dropblock_prepare_f32": 3, "odwscl_roi_align_fwd_f32": 1,
     "odwscl_roi_align_bwd_f32": 1, "odwscl_roi_align_fwd_nhwc_f32": 1, "odwscl_roi_align_bwd_nhwc_f32": 1, "odwscl_box_iou_f32": 1, "odwscl_nms_f32": 1, "odwscl_nms_legacy_f32": 1,
     "odwscl_discover_phase_a_f32": 2, "odwscl_discover_phase_b_f32": 2, "odwscl_bank_assemble": 1,
-    "odwscl_supcon_fwd_f32": 2, "odwscl_supcon_bwd_f32": 1, "odwscl_od_layer_f32": 1,
+    "odwscl_supcon_fwd_f32": 2, "odwscl_supcon_bwd_f32": 1, "odwscl_supcon_tc_fwd_f32": 4, "odwscl_supcon_tc_bwd_f32": 4, "odwscl_od_layer_f32": 1,
     "odwscl_dropblock_f32": 3, "odwscl_dropblock_rows_f32": 3, "odwscl_dropblock_seg_f32": 2, "odwscl_dropblock_mask_f32": 1, "odwscl_sim_nxn_f32": 2, "odwscl_gemm_nt_tf32": 1,
     "odwscl_conv3x3_nhwc_tf32": 1, "odwscl_conv3x3_wgrad_nhwc_tf32": 2, "odwscl_conv3x3_c3_f32": 1, "odwscl_maxpool2x2_nhwc_f32": 1,
     "odwscl_maxpool2x2_nhwc_bwd_f32": 1, "odwscl_split_tf32": 1,
@@ -64,6 +64,9 @@ _SIGS = {
     "odwscl_bank_assemble": (_I, [_P, _P, _I, _I, _I, _I, _I] + [_P] * 8 + [_I] + [_P] * 4 + [_P]),
     "odwscl_supcon_fwd_f32": (_I, [_P, _P, _I, _P, _P, _P, _P, _I, _F, _P, _P, _P]),
     "odwscl_supcon_bwd_f32": (_I, [_P, _P, _I, _P, _P, _P, _P, _I, _F, _P, _P, _P, _P, _P]),
+    "odwscl_supcon_tc_ws_bytes": (_Z, [_I]),
+    "odwscl_supcon_tc_fwd_f32": (_I, [_P, _P, _I, _P, _P, _P, _P, _I, _F, _P, _Z, _P, _P, _P]),
+    "odwscl_supcon_tc_bwd_f32": (_I, [_I, _P, _P, _P, _P, _I, _F, _P, _Z, _P, _P, _P, _P, _P]),
     "odwscl_od_layer_f32": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _I, _P, _P, _F, _P, _P, _P, _P]),
     "odwscl_dropblock_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P]),
     "odwscl_dropblock_rows_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P]),
@@ -915,6 +918,29 @@ def supcon_forward(F, E, row_src, row_lab, row_w, M_dev, Mcap, inv_temp):
         _call("odwscl_supcon_fwd_f32", _ptr(F), _ptr(E), F.shape[0], _ptr(row_src), _ptr(row_lab), _ptr(row_w),
               _ptr(M_dev), Mcap, float(inv_temp), _ptr(stats), _ptr(loss), _stream())
     return loss, stats
+
+
+def supcon_tc_forward(F, E, row_src, row_lab, row_w, M_dev, Mcap, inv_temp):
+    """SupCon forward with S = V V^T on the tensor cores (3xTF32 via fc_gemm); returns (loss, stats, ws) -- `ws` carries S to
+    supcon_tc_backward."""
+    dev = F.device
+    stats = torch.empty(((1 + SUPCON_SPLITS) * max(Mcap, 1), 4), dtype=torch.float32, device=dev)
+    loss = torch.zeros((1,), dtype=torch.float32, device=dev)
+    nbytes = int(lib().odwscl_supcon_tc_ws_bytes(int(Mcap)))
+    ws = torch.empty((max(nbytes, 16) // 4,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _call("odwscl_supcon_tc_fwd_f32", _ptr(F), _ptr(E), F.shape[0], _ptr(row_src), _ptr(row_lab), _ptr(row_w),
+              _ptr(M_dev), Mcap, float(inv_temp), _ptr(ws), nbytes, _ptr(stats), _ptr(loss), _stream())
+    return loss, stats, ws
+
+
+def supcon_tc_backward(F, E, row_src, row_lab, row_w, M_dev, Mcap, inv_temp, stats, gscale, ws):
+    dF = torch.zeros_like(F)
+    dE = torch.zeros_like(E) if E is not None and E.numel() else None
+    with torch.cuda.device(F.device):
+        _call("odwscl_supcon_tc_bwd_f32", F.shape[0], _ptr(row_src), _ptr(row_lab), _ptr(row_w), _ptr(M_dev), Mcap,
+              float(inv_temp), _ptr(ws), ws.numel() * 4, _ptr(stats), _ptr(gscale), _ptr(dF), _ptr(dE), _stream())
+    return dF, dE
 
 
 def supcon_backward(F, E, row_src, row_lab, row_w, M_dev, Mcap, inv_temp, stats, gscale):

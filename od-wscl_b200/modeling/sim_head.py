@@ -2,6 +2,8 @@
 State-dict keys: roi_heads.model_sim.mlp.{0,2}.  The loss runs as the fused kernels of
 csrc/supcon.cu (forward and backward), fed by a row-id list into [F ; E] instead of a concatenated
 bank."""
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -55,13 +57,23 @@ class Sim_Net(nn.Module):
                                          role=role if st is not None else None))
 
 
+# Banks of at least this many rows (bound Mcap) take the tensor-core path (csrc/supcon_tc.cu: both M x M contractions
+# as 3xTF32 tcgen05 GEMMs); smaller ones the fused FFMA tile kernels (csrc/supcon.cu: 3 launches, nothing in HBM).
+SUPCON_TC_MIN_ROWS = int(os.environ.get("ODWSCL_SUPCON_TC_MIN", "3072"))   # measured crossover: profiles/r02_supcon.txt
+
+
 class _SupConBankFn(Function):
     """loss = mean_r( -log(pos_r / all_r) * w_r ) over the bank rows V[row_src], V = [Fm ; E]."""
 
     @staticmethod
     def forward(ctx, Fm, E, row_src, row_lab, row_w, M_dev, Mcap, inv_temp):
         Fm, E = Fm.contiguous(), E.contiguous()
-        loss, stats = capi.supcon_forward(Fm, E, row_src, row_lab, row_w, M_dev, Mcap, inv_temp)
+        ctx.tc = Mcap >= SUPCON_TC_MIN_ROWS
+        if ctx.tc:
+            loss, stats, ws = capi.supcon_tc_forward(Fm, E, row_src, row_lab, row_w, M_dev, Mcap, inv_temp)
+            ctx.ws = ws                                        # S and the split bank rows: consumed by the one backward
+        else:
+            loss, stats = capi.supcon_forward(Fm, E, row_src, row_lab, row_w, M_dev, Mcap, inv_temp)
         ctx.save_for_backward(Fm, E, row_src, row_lab, row_w, M_dev, stats)
         ctx.Mcap, ctx.inv_temp = Mcap, inv_temp
         return loss.view(())
@@ -71,7 +83,13 @@ class _SupConBankFn(Function):
     def backward(ctx, g):
         Fm, E, row_src, row_lab, row_w, M_dev, stats = ctx.saved_tensors
         g = g.contiguous().view(1).float()
-        dF, dE = capi.supcon_backward(Fm, E, row_src, row_lab, row_w, M_dev, ctx.Mcap, ctx.inv_temp, stats, g)
+        if ctx.tc:
+            ws, ctx.ws = ctx.ws, None                          # H overwrites S: a second backward would need a new forward
+            if ws is None:
+                raise RuntimeError("SupCon (tensor-core path): backward called twice on the same graph")
+            dF, dE = capi.supcon_tc_backward(Fm, E, row_src, row_lab, row_w, M_dev, ctx.Mcap, ctx.inv_temp, stats, g, ws)
+        else:
+            dF, dE = capi.supcon_backward(Fm, E, row_src, row_lab, row_w, M_dev, ctx.Mcap, ctx.inv_temp, stats, g)
         return dF, dE, None, None, None, None, None, None
 
 

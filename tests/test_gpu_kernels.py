@@ -240,8 +240,17 @@ def test_nms_empty(capi):
 
 
 # ------------------------------------------------------------------------------- SupCon
+@pytest.fixture(params=["tiles", "tensor"])
+def supcon_path(request, monkeypatch):
+    """Both SupCon implementations: the fused FFMA tile kernels (csrc/supcon.cu) and the tcgen05 3xTF32 path
+    (csrc/supcon_tc.cu), which the host picks for banks of >= SUPCON_TC_MIN_ROWS rows."""
+    from odwscl_b200.modeling import sim_head
+    monkeypatch.setattr(sim_head, "SUPCON_TC_MIN_ROWS", 0 if request.param == "tensor" else 1 << 30)
+    return request.param
+
+
 @pytest.mark.parametrize("tag", ["a", "b"])
-def test_supcon_golden(capi, golden, tag):
+def test_supcon_golden(capi, golden, tag, supcon_path):
     """fp32 loss within 1e-4 rel (north_star tolerance), gradient within 2e-4 rel."""
     from odwscl_b200.modeling.sim_head import supcon_bank_loss
     G = golden("supcon.npz")
@@ -257,7 +266,7 @@ def test_supcon_golden(capi, golden, tag):
     np.testing.assert_allclose(f.grad.cpu().numpy(), G[tag + "_grad"], rtol=2e-3, atol=2e-8)
 
 
-def test_supcon_module_duplicates(capi):
+def test_supcon_module_duplicates(capi, supcon_path):
     """bank rows that repeat a source row (the [m] fallback, loss.py:338) accumulate their grads."""
     from odwscl_b200.modeling.sim_head import supcon_bank_loss
     g = torch.Generator().manual_seed(3)
@@ -277,6 +286,35 @@ def test_supcon_module_duplicates(capi):
     assert abs(float(loss) - float(ref)) <= 1e-4 * abs(float(ref))
     np.testing.assert_allclose(Fg.grad.cpu().numpy(), Fc.grad.numpy(), rtol=2e-3, atol=1e-7)
     np.testing.assert_allclose(Eg.grad.cpu().numpy(), Ec.grad.numpy(), rtol=2e-3, atol=1e-7)
+
+
+@pytest.mark.parametrize("M,Mcap", [(3000, 3072), (2051, 2051), (1, 4)])
+def test_supcon_large_bank_vs_oracle(capi, M, Mcap, supcon_path):
+    """Bank sizes of 8 images per rank (configs[2]); M not a multiple of the tile sizes, padded bound > M, repeated source
+    rows, rows from both F and E; a one-row bank (no other rows: the reference's 0/0) must give the same non-finite loss."""
+    from odwscl_b200.modeling.sim_head import supcon_bank_loss
+    g = torch.Generator().manual_seed(M)
+    nF, nE = max(1, M // 2), max(1, M // 4)
+    Fm = torch.nn.functional.normalize(torch.randn(nF, 128, generator=g), dim=1)
+    E = torch.nn.functional.normalize(torch.randn(nE, 128, generator=g), dim=1)
+    src = torch.randint(0, nF + nE, (M,), generator=g)
+    lab = torch.randint(0, 6, (M,), generator=g)
+    w = torch.rand(M, generator=g)
+    Fc, Ec = Fm.clone().requires_grad_(True), E.clone().requires_grad_(True)
+    ref = orc.supcon_v2(torch.cat([Fc, Ec])[src], lab.float(), w, 0.2)
+    pad = torch.zeros(Mcap - M, dtype=torch.int32)
+    Fg, Eg = Fm.cuda().requires_grad_(True), E.cuda().requires_grad_(True)
+    loss = supcon_bank_loss(Fg, Eg, torch.cat([src.int(), pad]).cuda(), torch.cat([lab.int(), pad]).cuda(),
+                            torch.cat([w, pad.float()]).cuda(), torch.full((1,), M, dtype=torch.int32, device="cuda"), Mcap, 0.2)
+    if M == 1:
+        assert not np.isfinite(float(ref)) and not np.isfinite(float(loss))
+        return
+    ref.backward()
+    loss.backward()
+    assert abs(float(loss) - float(ref)) <= 1e-4 * abs(float(ref))
+    scale = float(Fc.grad.abs().max())
+    np.testing.assert_allclose(Fg.grad.cpu().numpy(), Fc.grad.numpy(), rtol=2e-3, atol=2e-4 * scale)
+    np.testing.assert_allclose(Eg.grad.cpu().numpy(), Ec.grad.numpy(), rtol=2e-3, atol=2e-4 * scale)
 
 
 # ------------------------------------------------------------------------------- DropBlock / sim
