@@ -236,3 +236,22 @@ def test_fc_gemm_second_operand_pair(capi):
         f = lambda t, mn: (t.T.contiguous() if mn else t).cuda()
         got = capi.fc_gemm(f(A, a_mn), f(B, b_mn), a_mn=a_mn, b_mn=b_mn, A2=f(A2, a_mn), B2=f(B2, b_mn)).cpu()
         torch.testing.assert_close(got, ref, rtol=1e-6, atol=2e-5 * (K1 + K2) ** 0.5)
+
+
+@pytest.mark.gpu
+def test_peer_gradient_sum_two_gpus():
+    """The fused weight-gradient GEMM + cross-rank sum (csrc/fc_gemm.cu kPeerSum, sharding.PeerGradSum) on 2 GPUs of one
+    NVSwitch box: kernel result == all-reduced local products (bit for bit), one model step's gradients == plain DDP's
+    (both forms: push to all, reduce-scatter + gather).  Needs 2 GPUs; the single-GPU round-end box skips it
+    (profiles/r02_peer_sum_check_n2.txt holds the 2-GPU run of this round)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29577", os.path.join(root, "scripts", "peer_sum_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "PEER_SUM_CHECK PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
