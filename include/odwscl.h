@@ -134,7 +134,7 @@ int odwscl_discover_phase_b_f32(const float* boxes, const int32_t* img_off, int 
 /* Bank assembly for SupConLossV2 (sim_head/sim_loss.py:55-58 + loss.py:290-345 append order):
  * rows class-major, weights in execution order (the reference's misalignment is reproduced).
  * row_src [Mcap] int32: < R -> row of F, else R + row of E; row_lab [Mcap] int32; row_w [Mcap];
- * M_out [1] int32. */
+ * M_out [2] int32: the rows written (min(M, Mcap)) and the unclamped M. */
 int odwscl_bank_assemble(const int32_t* pair_img, const int32_t* pair_cls, int P, int B, int R,
                          int Ncap, int num_fg_classes, const int32_t* img_off, const int32_t* cntA,
                          const int32_t* offA, const int32_t* rowsA, const float* hardA,

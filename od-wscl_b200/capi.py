@@ -901,7 +901,7 @@ def bank_assemble(st, num_fg_classes, Mcap):
     st.row_src = torch.empty((max(Mcap, 1),), dtype=torch.int32, device=dev)
     st.row_lab = torch.empty((max(Mcap, 1),), dtype=torch.int32, device=dev)
     st.row_w = torch.empty((max(Mcap, 1),), dtype=torch.float32, device=dev)
-    st.M = torch.zeros((1,), dtype=torch.int32, device=dev)
+    st.M = torch.zeros((2,), dtype=torch.int32, device=dev)     # rows written (<= Mcap), unclamped row count
     with torch.cuda.device(dev):
         _call("odwscl_bank_assemble", _ptr(st.pair_img), _ptr(st.pair_cls), st.P, st.B, st.R, st.Ncap,
               int(num_fg_classes), _ptr(st.img_off), _ptr(st.cntA), _ptr(st.offA), _ptr(st.rowsA), _ptr(st.hardA),

@@ -385,7 +385,8 @@ bank_assemble_kernel(const int32_t* __restrict__ pair_img, const int32_t* __rest
       q0 = q1;
     }
     s_nb = nb; s_nw = nw;
-    *M_out = dst < Mcap ? dst : Mcap;
+    M_out[0] = dst < Mcap ? dst : Mcap;
+    M_out[1] = dst;                                       // unclamped: the caller sees a bound that was too small
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -588,7 +589,7 @@ ODW_API int odwscl_bank_assemble(const int32_t* pair_img, const int32_t* pair_cl
   if (P < 0 || P > kMaxPairs || Mcap < 0) return ODWSCL_EINVAL;
   if (!M_out) return ODWSCL_EINVAL;
   if (P == 0) {
-    ODW_CUDA(cudaMemsetAsync(M_out, 0, sizeof(int32_t), (cudaStream_t)stream));
+    ODW_CUDA(cudaMemsetAsync(M_out, 0, 2 * sizeof(int32_t), (cudaStream_t)stream));
     return 0;
   }
   if (!pair_img || !pair_cls || !img_off || !offA || !rowsA || !hardA || !newl || !new_cnt || !hardB || !row_src ||

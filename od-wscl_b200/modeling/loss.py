@@ -19,6 +19,7 @@ import torch.nn.functional as F
 from .. import capi
 from ..config import cfg as global_cfg
 from . import registry
+from . import sim_head
 from .sim_head import SupConLossV2, supcon_bank_loss
 
 
@@ -122,6 +123,7 @@ class RoIRegLossComputation(object):
         self.k_granule = 256
         self.overflow = None
         self._k_cap = None
+        self._m_cap, self._m_host, self._m_event = None, None, None
         self._k_host = None
         self._k_event = None
         self._stage_i32 = _PinnedStaging()
@@ -170,12 +172,22 @@ class RoIRegLossComputation(object):
         else:
             E, K = self._augmented_positives_synced(st, P, clean_pooled_feats, feature_extractor, model_sim)
         capi.discover_phase_b(st, Fm.detach(), E.detach(), self.nms)
-        Mcap = 3 * K + 3 * sum(sizes[b] for b in pair_img)
+        Mcap = 3 * K + 3 * sum(sizes[b] for b in pair_img)      # what the rule can produce at most: usually >> M
+        # Large banks (8 images per rank) go to the tensor-core SupCon, whose cost is Mcap^2: it gets a bound from the row
+        # counts read back so far (non-blocking, like K); a bank that outgrows it raises `overflow` and the step is redone.
+        m_cap = self._poll_m_cap() if spec else None
+        use_tc = m_cap is not None and min(m_cap, Mcap) >= sim_head.SUPCON_TC_MIN_ROWS
+        if use_tc:
+            Mcap = min(m_cap, Mcap)
         capi.bank_assemble(st, C - 1, Mcap)
+        if spec:
+            self._record_m(st.M[1:2])
+            if use_tc:
+                self.overflow = torch.maximum(self.overflow, (st.M[1:2] > Mcap).to(self.overflow.dtype))
         st.E = E.detach()                       # [2K,128] augmented-positive embeddings (drop rows, then noise rows)
         self.last_state = st
         loss_sim = self.sim_lmda * supcon_bank_loss(Fm, E, st.row_src, st.row_lab, st.row_w, st.M, Mcap,
-                                                    self.temp)                         # loss.py:347
+                                                    self.temp, tc=use_tc)              # loss.py:347
         # ---- pseudo labels (loss.py:364-368 -> od_layer) and the MIL + refinement losses (loss.py:349-406)
         pl, lw, rt = capi.od_layer(st, self.fg_thresh)
         out = _HeadLossFn.apply(logits, hs, img_labels_d, pl, lw, rt, bool(self.cls_agnostic_bbox_reg), float(epsilon))
@@ -196,6 +208,22 @@ class RoIRegLossComputation(object):
             self._k_cap = cap if self._k_cap is None else max(self._k_cap, cap)
             self._k_event = None
         return self._k_cap
+
+    def _poll_m_cap(self):
+        """Bound on the SupCon bank rows from the counts read back so far (margin 1.25, grid of 256)."""
+        if self._m_event is not None and self._m_event.query():
+            cap = (int(int(self._m_host[0]) * 1.25) + 255) // 256 * 256
+            self._m_cap = cap if self._m_cap is None else max(self._m_cap, cap)
+            self._m_event = None
+        return self._m_cap
+
+    def _record_m(self, mdev):
+        if self._m_host is None:
+            self._m_host = torch.zeros((1,), dtype=torch.int32).pin_memory()
+        if self._m_event is None:                      # one readback in flight at a time
+            self._m_host.copy_(mdev, non_blocking=True)
+            self._m_event = torch.cuda.Event()
+            self._m_event.record()
 
     def _cap_for(self, k):
         """Bound for a batch of k positives: margin, then a coarse grid so the padded shapes (GEMM heuristics, allocator

@@ -66,9 +66,9 @@ class _SupConBankFn(Function):
     """loss = mean_r( -log(pos_r / all_r) * w_r ) over the bank rows V[row_src], V = [Fm ; E]."""
 
     @staticmethod
-    def forward(ctx, Fm, E, row_src, row_lab, row_w, M_dev, Mcap, inv_temp):
+    def forward(ctx, Fm, E, row_src, row_lab, row_w, M_dev, Mcap, inv_temp, tc):
         Fm, E = Fm.contiguous(), E.contiguous()
-        ctx.tc = Mcap >= SUPCON_TC_MIN_ROWS
+        ctx.tc = (Mcap >= SUPCON_TC_MIN_ROWS) if tc is None else bool(tc)
         if ctx.tc:
             loss, stats, ws = capi.supcon_tc_forward(Fm, E, row_src, row_lab, row_w, M_dev, Mcap, inv_temp)
             ctx.ws = ws                                        # S and the split bank rows: consumed by the one backward
@@ -90,11 +90,13 @@ class _SupConBankFn(Function):
             dF, dE = capi.supcon_tc_backward(Fm, E, row_src, row_lab, row_w, M_dev, ctx.Mcap, ctx.inv_temp, stats, g, ws)
         else:
             dF, dE = capi.supcon_backward(Fm, E, row_src, row_lab, row_w, M_dev, ctx.Mcap, ctx.inv_temp, stats, g)
-        return dF, dE, None, None, None, None, None, None
+        return dF, dE, None, None, None, None, None, None, None
 
 
-def supcon_bank_loss(Fm, E, row_src, row_lab, row_w, M_dev, Mcap, temperature):
-    return _SupConBankFn.apply(Fm, E, row_src, row_lab, row_w, M_dev, Mcap, 1.0 / temperature)
+def supcon_bank_loss(Fm, E, row_src, row_lab, row_w, M_dev, Mcap, temperature, tc=None):
+    """tc: None = by size (Mcap >= SUPCON_TC_MIN_ROWS: right when Mcap is the row count or a tight bound on it); the
+    tensor-core path works on all Mcap x Mcap entries, so a caller with a loose bound decides itself (weak_head/loss.py)."""
+    return _SupConBankFn.apply(Fm, E, row_src, row_lab, row_w, M_dev, Mcap, 1.0 / temperature, tc)
 
 
 class SupConLossV2(nn.Module):

@@ -305,6 +305,27 @@ def test_speculative_k_matches_synced():
     for k in ref_g:
         a = 0.1 if "model_sim" in k else 1e-3
         torch.testing.assert_close(got_g[k], ref_g[k], rtol=2e-4, atol=a * float(ref_g[k].abs().max()) + 1e-9)
+    # the same step with SupCon on its tensor-core path (production: banks of >= 3072 rows; forced here): the bank bound
+    # then comes from the row counts read back so far, and the loss / gradients agree with the tile kernels
+    from odwscl_b200.modeling import sim_head
+    M = int(ev.last_state.M[1])
+    assert M == int(ev.last_state.M[0]) and ev._poll_m_cap() is not None and ev._m_cap >= M
+    old_thr, sim_head.SUPCON_TC_MIN_ROWS = sim_head.SUPCON_TC_MIN_ROWS, 64
+    try:
+        tc_l, tc_g = run()
+        assert float(ev.overflow) == 0.0
+        assert abs(tc_l["loss_sim"] - got_l["loss_sim"]) <= 1e-5 * abs(got_l["loss_sim"])
+        for k in ref_g:
+            a = 0.1 if "model_sim" in k else 1e-3
+            torch.testing.assert_close(tc_g[k], got_g[k], rtol=2e-4, atol=a * float(got_g[k].abs().max()) + 1e-9)
+        ev._m_cap, ev._m_event = 64, None          # bank bound too small: flagged, finite
+        bad_l, _ = run()
+        assert float(ev.overflow) == 1.0 and int(ev.last_state.M[0]) == 64 and int(ev.last_state.M[1]) == M
+        assert all(np.isfinite(v) for v in bad_l.values())
+        torch.cuda.synchronize()
+        assert ev._poll_m_cap() >= M               # ... and the read-back raises the bound for the redo
+    finally:
+        sim_head.SUPCON_TC_MIN_ROWS = old_thr
     ev._k_cap = 1                                  # bound too small: flagged, finite, nothing out of range
     ev._k_event = None
     bad_l, _ = run()
