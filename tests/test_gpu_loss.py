@@ -154,7 +154,7 @@ def test_discovery_stagewise_vs_oracle_random(sizes, pos):
                   [emb[(pair_img[p], pair_cls[p], "noise")] for p in range(P)]).cuda()
     capi.discover_phase_b(st, simf.cuda(), E, 0.1)
     capi.bank_assemble(st, C - 1, 3 * K + 3 * sum(sizes[b] for b in pair_img))
-    M = int(st.M.item())
+    M = int(st.M[0])
     instd, cnt = st.inst.cpu().numpy(), st.inst_cnt.cpu().numpy()
     tau = st.tau.cpu().numpy()
     for p in range(P):
