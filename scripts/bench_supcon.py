@@ -9,8 +9,14 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from odwscl_b200 import capi                      # noqa: E402
 from odwscl_b200.modeling import sim_head         # noqa: E402
 
+import argparse                                   # noqa: E402
+ap = argparse.ArgumentParser()
+ap.add_argument("--M", type=int, nargs="*", default=[1100, 2048, 4096, 6000])
+ap.add_argument("--iters", type=int, default=6)
+ap.add_argument("--paths", nargs="*", default=["tiles", "tensor"])       # for ncu captures: --M 6000 --iters 3 --paths tensor
+args = ap.parse_args()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-for M in (1100, 2048, 4096, 6000):
+for M in args.M:
     g = torch.Generator(device="cuda").manual_seed(M)
     Fm = torch.nn.functional.normalize(torch.randn(M, 128, device="cuda", generator=g), dim=1).requires_grad_(True)
     E = torch.zeros(1, 128, device="cuda")
@@ -20,9 +26,12 @@ for M in (1100, 2048, 4096, 6000):
     Md = torch.full((1,), M, dtype=torch.int32, device="cuda")
     out = {}
     for name, thr in (("tiles", 1 << 30), ("tensor", 0)):
+        if name not in args.paths:
+            out[name] = (float("nan"),) * 4
+            continue
         sim_head.SUPCON_TC_MIN_ROWS = thr
         ts = []
-        for it in range(6):
+        for it in range(args.iters):
             flush.zero_()
             Fm.grad = None
             a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
@@ -33,7 +42,7 @@ for M in (1100, 2048, 4096, 6000):
             c.record()
             torch.cuda.synchronize()
             ts.append((a.elapsed_time(b), b.elapsed_time(c)))
-        out[name] = (min(t[0] for t in ts[2:]), min(t[1] for t in ts[2:]), float(loss), float(Fm.grad.abs().max()))
+        out[name] = (min(t[0] for t in ts[-4:]), min(t[1] for t in ts[-4:]), float(loss), float(Fm.grad.abs().max()))
     f = 2.0 * M * M * 128
     print("M %5d  tiles fwd %.3f bwd %.3f ms | tensor fwd %.3f bwd %.3f ms | loss %.6f / %.6f  max|grad| %.3e / %.3e  "
           "(2 M^2 128 = %.1f GFLOP per contraction)" % (M, out["tiles"][0], out["tiles"][1], out["tensor"][0], out["tensor"][1],
