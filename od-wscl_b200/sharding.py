@@ -146,7 +146,9 @@ class PeerGradSum:
     tiles to all replicas from its epilogue (csrc/fc_gemm.cu kPeerSum, multimem.red), and two rank barriers per step --
     before the optimizer reads, after it has zeroed -- are the only synchronisation.  fc6 + fc7 + Sim_Net are 536 of the
     611 MB a step all-reduces; what is left goes through DistributedDataParallel as before.
-    Gradients of these weights are complete only after `before_step()` (the optimizer hooks call it).
+    Gradients of these weights are complete only after `before_step()` (the optimizer hooks call it), and they are
+    cleared by `after_step()`, not by `optimizer.zero_grad()`: a backward whose gradients are discarded without an
+    optimizer step must be followed by `after_step()` on every rank.
 
     Two forms.  world <= PEER_PUSH_ALL_MAX: every tile goes to EVERY replica (multimem.red, one NVLink operation replicated
     by the switch) and nothing else is needed -- measured at 2 GPUs: 17.6 ms/step against 18.2-18.5 with the all-reduce.
@@ -239,12 +241,15 @@ def wrap_ddp(model, device=None):
         try:
             peer = PeerGradSum([p for _, p in cand], device)
             torch.nn.parallel.DistributedDataParallel._set_params_and_buffers_to_ignore_for_model(model, [n for n, _ in cand])
+            for _, p in cand:                                   # DDP's initial rank-0 broadcast skips ignored parameters
+                dist.broadcast(p.data, src=0)
         except Exception as e:                                  # no NVLS: everything stays on the bucket all-reduce
             if dist.get_rank() == 0:
                 print("[od-wscl_b200] peer gradient sum unavailable (%s); all gradients use the DDP all-reduce" % (e,), flush=True)
             for _, p in cand:
                 if hasattr(p, "_odw_peer"):
                     del p._odw_peer
+            model._ddp_params_and_buffers_to_ignore = []
             peer = None
     ddp = MarginedDDP(model, device_ids=ids, broadcast_buffers=False, static_graph=True, bucket_cap_mb=bucket_mb,
                       gradient_as_bucket_view=True, sm_margin=margin)
