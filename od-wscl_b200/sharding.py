@@ -1,7 +1,8 @@
 """Multi-GPU host logic of the hot path: images shard across ranks, the rank-local contrastive bank
 stays local (modeling/roi_heads/weak_head/loss.py:276-347 only sees the rank's own targets/proposals), and the one
-exchange per step is the gradient all-reduce (tools/train_net.py:50-55).  One process per GPU; `torch.distributed`
-(NCCL on the GPU box, gloo in the CPU tests) is the plumbing."""
+exchange per step is the gradient sum (tools/train_net.py:50-55): DistributedDataParallel's bucket all-reduce, with the
+big fully-connected weight gradients optionally summed across ranks by the weight-gradient GEMM itself (PeerGradSum).
+One process per GPU; `torch.distributed` (NCCL on the GPU box, gloo in the CPU tests) is the plumbing."""
 import os
 
 import torch
