@@ -154,3 +154,30 @@ def test_multi_gpu_plan(monkeypatch):
             for t in spans:                                  # the kernel's rule: owner = min(row0 // rpo, world - 1)
                 for r in range(*t.own):
                     assert min((r // 32 * 32) // rpo, world - 1) == t.owner.rank
+
+
+def test_peer_target_hands_the_gradient_view_once_per_step():
+    """fc._LinearFn.backward returns `_PeerTarget.grad()` for a peer-summed weight: the buffer slice the first time in a
+    step (autograd adopts it as .grad), None for a second gradient of the same weight in that step and whenever .grad
+    already IS the buffer (otherwise autograd would add the buffer to itself); after_step() re-arms it."""
+    import torch
+    from odwscl_b200 import sharding
+
+    class _Owner:
+        world, rank, scatter, scale = 2, 0, False, 0.5
+
+        def __init__(self):
+            self.handed = {}
+    owner = _Owner()
+    buf = torch.zeros(64 * 8)
+    p = torch.nn.Parameter(torch.zeros(64, 8))
+    t = sharding._PeerTarget(owner, p, buf.view(64, 8), 0, [0, 0])
+    g1 = t.grad()
+    assert g1 is not None and g1.data_ptr() == buf.data_ptr() and g1 is not t.view     # a fresh view object of the buffer
+    assert t.grad() is None                                                            # second product of the step
+    p.grad = g1
+    owner.handed.clear()                                                               # what after_step() does
+    assert t.grad() is None                                                            # .grad already is the buffer
+    p.grad = None                                                                      # zero_grad(set_to_none=True)
+    g2 = t.grad()
+    assert g2 is not None and g2.data_ptr() == buf.data_ptr()
