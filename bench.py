@@ -344,6 +344,11 @@ def run_ours(args):
     torch.backends.cudnn.allow_tf32 = not args.strict_fp32
     torch.backends.cudnn.benchmark = True
     capi.lib()
+    # The host side of a step is a handful of tiny CPU tensor ops (labels, offsets, staging): one intra-op thread, so no
+    # OpenMP pool spins beside the enqueueing thread (torchrun exports OMP_NUM_THREADS=1 anyway; the CPU arm sets its own
+    # count).  It does not remove the 40-100 ms host stalls some boxes show (a 16-core host shared between pods: the
+    # enqueueing thread is descheduled in the middle of plain Python between two launches) -- see timed_window().
+    torch.set_num_threads(int(os.environ.get("ODWSCL_HOST_THREADS", "1")))
 
     from odwscl_b200.config import get_cfg_defaults
     mcfg = get_cfg_defaults()
